@@ -1,0 +1,97 @@
+"""ctypes front-ends of the TEST INFRASTRUCTURE libraries (never imported by tengine_b200/):
+
+  Oracle        oracle/libtb200_oracle.so   the CPU restatement (tb200_oracle.c)
+  Reference     oracle/_ref/libref_shim.so  the unmodified reference driven through ref_shim.c
+
+Both consume a tengine_b200.graphdef.GraphDef and host NCHW numpy arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(quiet=True):
+    """Compile the C restatement (and, when /root/reference exists, oracle/_ref). Building the checker is not
+    using it."""
+    r = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    if not quiet:
+        print(r.stdout[-800:])
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(HERE, "libtb200_oracle.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = C.CDLL(path)
+        self.lib.tb200_oracle_run.restype = C.c_int
+        self.lib.tb200_oracle_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+
+    def run(self, g, inputs, uint8_mode=0):
+        """Run every layer; returns the list of all tensors (numpy NCHW), index = tensor id."""
+        T, L = g.c_tables()
+        bufs = [np.zeros(g.dims(i), dtype=g.np_dtype) for i in range(len(g.tensors))]
+        for t, x in zip(g.inputs, inputs):
+            assert x.shape == g.dims(t) and x.dtype == g.np_dtype, (x.shape, g.dims(t), x.dtype)
+            bufs[t] = np.ascontiguousarray(x)
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        rc = self.lib.tb200_oracle_run(T, len(g.tensors), L, len(g.layers), ptrs, uint8_mode)
+        if rc != 0:
+            raise RuntimeError(f"oracle failed at layer {-rc - 1}")
+        return bufs
+
+
+class Reference:
+    """The unmodified reference (OAID/Tengine CPU device, or any device registered in the loaded library)."""
+
+    def __init__(self, libdir=None):
+        libdir = libdir or os.path.join(HERE, "_ref")
+        shim = os.path.join(libdir, "libref_shim.so")
+        if not os.path.exists(shim):
+            raise FileNotFoundError(f"{shim} missing: run `make -C oracle` where /root/reference exists")
+        C.CDLL(os.path.join(libdir, "libtengine-lite.so"), mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(shim)
+        self.lib.ref_shim_run.restype = C.c_int
+        self.lib.ref_shim_version.restype = C.c_char_p
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_shim.so"))
+
+    def version(self):
+        return self.lib.ref_shim_version().decode()
+
+    def run(self, g, inputs, want=None, device=None, threads=None, warmup=0, loops=1, env=None):
+        """Returns ({tensor_id: array}, (min_ms, avg_ms)).  `want` defaults to g.outputs.
+        env e.g. {"TG_DEBUG_REF": "1"} (cpu_module.c:158-166: force the naive reference kernels)."""
+        want = list(g.outputs if want is None else want)
+        T, L = g.c_tables()
+        ins = [np.ascontiguousarray(x) for x in inputs]
+        outs = [np.zeros(g.dims(t), dtype=g.np_dtype) for t in want]
+        inp = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+        outp = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
+        stats = (C.c_double * 2)()
+        saved = {}
+        for k, v in (env or {}).items():
+            saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        try:
+            rc = self.lib.ref_shim_run(T, len(g.tensors), L, len(g.layers), g.id_array(g.inputs), len(g.inputs),
+                                       g.id_array(want), len(want), inp, outp,
+                                       device.encode() if device else None, threads or (os.cpu_count() or 1),
+                                       warmup, loops, stats)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        if rc != 0:
+            raise RuntimeError(f"reference run failed rc={rc}")
+        return dict(zip(want, outs)), (stats[0], stats[1])

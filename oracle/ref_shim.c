@@ -1,0 +1,309 @@
+/*
+ * ref_shim.c -- drive the UNMODIFIED reference (oracle/_ref/libtengine-lite.so) from this repo's layer
+ * descriptors.  TEST INFRASTRUCTURE ONLY (see oracle/tb200_oracle.c header).
+ *
+ * It builds a Tengine graph through the reference's public C API exactly the way the reference's own
+ * per-device op tests do (tests/op/test_op.h:619-664 create_common_test_graph, tests/op/
+ * test_timvx_op_convolution.cpp:32-93: create_graph_node + Const nodes + node->op.param_mem), runs it on a
+ * named device (default: the reference CPU device) and returns the requested tensors.  It is used to
+ *   (1) pin oracle/tb200_oracle.c against the real reference on seeded inputs,
+ *   (2) generate tests/golden/ fixtures (tests/golden/make_golden.py),
+ *   (3) time the reference CPU backend for bench.py --impl reference / cpu_baseline,
+ *   (4) run the same graph on the "B200" device when the integration library is loaded instead.
+ * Compiled against the reference headers where they lie (never copied): see oracle/Makefile.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include "api/c_api.h"
+#include "graph/graph.h"
+#include "graph/node.h"
+#include "graph/tensor.h"
+#include "operator/prototype/convolution_param.h"
+#include "operator/prototype/pooling_param.h"
+#include "operator/prototype/fc_param.h"
+#include "operator/prototype/relu_param.h"
+#include "operator/prototype/eltwise_param.h"
+#include "operator/prototype/concat_param.h"
+#include "operator/prototype/upsample_param.h"
+
+#include "../include/tengine_b200.h"
+
+#define SHIM_API __attribute__((visibility("default")))
+
+static int g_inited = 0;
+
+static double now_ms(void)
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec * 1000.0 + tv.tv_usec / 1000.0;
+}
+
+static tensor_t make_const(graph_t graph, const char* name, int dtype, const int* dims, int ndim, const void* data,
+                           int bytes, const float* scales, const int* zps, int nq)
+{
+    node_t node = create_graph_node(graph, name, "Const");
+    tensor_t t = create_graph_tensor(graph, name, dtype);
+    if (!node || !t) return NULL;
+    set_node_output_tensor(node, 0, t, TENSOR_TYPE_CONST);
+    set_tensor_shape(t, dims, ndim);
+    if (set_tensor_buffer(t, (void*)data, bytes) < 0) return NULL;
+    if (nq > 0) set_tensor_quant_param(t, scales, zps, nq);
+    return t;
+}
+
+/* Returns 0 on success.  `want_ids` tensors (must be layer outputs) are marked graph outputs and copied to
+ * out_bufs after the last run.  ms_stats[0]=min, [1]=avg over `loops` timed run_graph calls (after `warmup`). */
+SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
+                          int num_layers, const int* input_ids, int num_inputs, const int* want_ids, int num_want,
+                          const void* const* in_bufs, void* const* out_bufs, const char* device_name,
+                          int num_thread, int warmup, int loops, double* ms_stats)
+{
+    int rc = -1;
+    if (!g_inited)
+    {
+        if (init_tengine() != 0) return -100;
+        g_inited = 1;
+    }
+    context_t ctx = NULL;
+    if (device_name && device_name[0] && strcmp(device_name, "CPU") != 0)
+    {
+        ctx = create_context("shim", 1);
+        if (set_context_device(ctx, device_name, NULL, 0) < 0)
+        {
+            fprintf(stderr, "ref_shim: device %s not registered\n", device_name);
+            return -101;
+        }
+    }
+    graph_t graph = create_graph(ctx, NULL, NULL);
+    if (!graph) return -102;
+    set_graph_layout(graph, TENGINE_LAYOUT_NCHW);
+
+    tensor_t* tt = (tensor_t*)calloc(num_tensors, sizeof(tensor_t));
+    char** out_node_name = (char**)calloc(num_tensors, sizeof(char*));
+    char name[64];
+    int precision = TENGINE_MODE_INT8;
+
+    for (int i = 0; i < num_inputs; i++)
+    {
+        const tb200_tensor_desc* d = &tensors[input_ids[i]];
+        snprintf(name, sizeof name, "in%d", input_ids[i]);
+        node_t node = create_graph_node(graph, name, "InputOp");
+        tensor_t t = create_graph_tensor(graph, name, d->data_type);
+        if (!node || !t) goto done;
+        set_node_output_tensor(node, 0, t, TENSOR_TYPE_INPUT);
+        set_tensor_shape(t, d->dims, 4);
+        set_tensor_quant_param(t, &d->scale, &d->zero_point, 1);
+        tt[input_ids[i]] = t;
+        out_node_name[input_ids[i]] = strdup(name);
+        if (d->data_type == TENGINE_DT_UINT8) precision = TENGINE_MODE_UINT8;
+    }
+
+    for (int li = 0; li < num_layers; li++)
+    {
+        const tb200_layer_desc* L = &layers[li];
+        const tb200_tensor_desc* din = &tensors[L->inputs[0]];
+        const tb200_tensor_desc* dout = &tensors[L->output];
+        const char* opname = NULL;
+        switch (L->op)
+        {
+        case TB200_OP_CONV: opname = "Convolution"; break;
+        case TB200_OP_FC: opname = "FullyConnected"; break;
+        case TB200_OP_POOL: opname = "Pooling"; break;
+        case TB200_OP_RELU: opname = "ReLU"; break;
+        case TB200_OP_ELTWISE: opname = "Eltwise"; break;
+        case TB200_OP_CONCAT: opname = "Concat"; break;
+        case TB200_OP_UPSAMPLE: opname = "Upsample"; break;
+        case TB200_OP_IDENTITY: opname = "Dropout"; break;
+        default: goto done;
+        }
+        snprintf(name, sizeof name, "L%d", li);
+        struct node* node = (struct node*)create_graph_node(graph, name, opname);
+        if (!node) goto done;
+        for (int k = 0; k < L->num_inputs; k++)
+        {
+            if (!tt[L->inputs[k]]) { fprintf(stderr, "ref_shim: layer %d input %d undefined\n", li, k); goto done; }
+            set_node_input_tensor(node, k, tt[L->inputs[k]]);
+        }
+        if (L->op == TB200_OP_CONV || L->op == TB200_OP_FC)
+        {
+            const int is_u8 = din->data_type == TENGINE_DT_UINT8;
+            const int oc = dout->dims[1];
+            int wdims[4], wn;
+            int wbytes;
+            if (L->op == TB200_OP_CONV)
+            {
+                wdims[0] = oc, wdims[1] = din->dims[1] / L->group, wdims[2] = L->kernel_h, wdims[3] = L->kernel_w;
+                wn = 4;
+                wbytes = wdims[0] * wdims[1] * wdims[2] * wdims[3];
+            }
+            else
+            {
+                wdims[0] = oc, wdims[1] = din->dims[1] * din->dims[2] * din->dims[3];
+                wn = 2;
+                wbytes = wdims[0] * wdims[1];
+            }
+            int* zps = (int*)calloc(oc, sizeof(int));
+            float* bscales = (float*)calloc(oc, sizeof(float));
+            snprintf(name, sizeof name, "L%d_w", li);
+            tensor_t wt;
+            if (is_u8)
+            {
+                int wz = L->weight_zero;
+                wt = make_const(graph, name, TENGINE_DT_UINT8, wdims, wn, L->weight, wbytes, L->weight_scales, &wz, 1);
+                bscales[0] = din->scale * L->weight_scales[0];
+            }
+            else
+            {
+                wt = make_const(graph, name, TENGINE_DT_INT8, wdims, wn, L->weight, wbytes, L->weight_scales, zps, oc);
+                for (int c = 0; c < oc; c++) bscales[c] = din->scale * L->weight_scales[c];
+            }
+            if (!wt) goto done;
+            set_node_input_tensor(node, 1, wt);
+            if (L->bias)
+            {
+                snprintf(name, sizeof name, "L%d_b", li);
+                int bd[1] = {oc};
+                tensor_t bt = make_const(graph, name, TENGINE_DT_INT32, bd, 1, L->bias, oc * 4, bscales, zps, is_u8 ? 1 : oc);
+                if (!bt) goto done;
+                set_node_input_tensor(node, 2, bt);
+            }
+            free(zps);
+            free(bscales);
+        }
+        snprintf(name, sizeof name, "L%d", li);
+        tensor_t ot = create_graph_tensor(graph, name, dout->data_type);
+        set_node_output_tensor(node, 0, ot, TENSOR_TYPE_VAR);
+        set_tensor_quant_param(ot, &dout->scale, &dout->zero_point, 1);
+        /* Requested tensors get the caller's buffer BEFORE prerun: the CPU device's memory pool only manages
+         * tensors whose data is still NULL (cpu_pool.c:290-291), so they are never recycled or run in place. */
+        for (int k = 0; k < num_want; k++)
+            if (want_ids[k] == L->output)
+            {
+                set_tensor_shape(ot, dout->dims, 4);
+                if (set_tensor_buffer(ot, out_bufs[k], dout->dims[0] * dout->dims[1] * dout->dims[2] * dout->dims[3]) < 0) goto done;
+            }
+        tt[L->output] = ot;
+        out_node_name[L->output] = strdup(name);
+
+        void* pm = node->op.param_mem;
+        switch (L->op)
+        {
+        case TB200_OP_CONV:
+        {
+            struct conv_param* p = (struct conv_param*)pm;
+            p->kernel_h = L->kernel_h, p->kernel_w = L->kernel_w, p->stride_h = L->stride_h, p->stride_w = L->stride_w;
+            p->pad_h0 = L->pad_h0, p->pad_h1 = L->pad_h1, p->pad_w0 = L->pad_w0, p->pad_w1 = L->pad_w1;
+            p->dilation_h = L->dilation_h, p->dilation_w = L->dilation_w;
+            p->input_channel = din->dims[1], p->output_channel = dout->dims[1], p->group = L->group;
+            p->activation = L->activation;
+            break;
+        }
+        case TB200_OP_FC: ((struct fc_param*)pm)->num_output = dout->dims[1]; break;
+        case TB200_OP_POOL:
+        {
+            struct pool_param* p = (struct pool_param*)pm;
+            p->pool_method = L->pool_method, p->global = L->pool_global, p->caffe_flavor = L->caffe_flavor;
+            p->kernel_h = L->kernel_h, p->kernel_w = L->kernel_w, p->stride_h = L->stride_h, p->stride_w = L->stride_w;
+            p->pad_h0 = p->pad_h0_org = L->pad_h0, p->pad_h1 = p->pad_h1_org = L->pad_h1;
+            p->pad_w0 = p->pad_w0_org = L->pad_w0, p->pad_w1 = p->pad_w1_org = L->pad_w1;
+            break;
+        }
+        case TB200_OP_RELU: ((struct relu_param*)pm)->negative_slope = L->negative_slope; break;
+        case TB200_OP_ELTWISE:
+        {
+            struct eltwise_param* p = (struct eltwise_param*)pm;
+            p->type = L->elt_type, p->caffe_flavor = 1;
+            break;
+        }
+        case TB200_OP_CONCAT: ((struct concat_param*)pm)->axis = L->axis; break;
+        case TB200_OP_UPSAMPLE: ((struct upsample_param*)pm)->scale = (float)L->up_scale; break;
+        default: break;
+        }
+    }
+
+    {
+        const char** names = (const char**)calloc(num_inputs + num_want, sizeof(char*));
+        for (int i = 0; i < num_inputs; i++) names[i] = out_node_name[input_ids[i]];
+        if (set_graph_input_node(graph, names, num_inputs) < 0) goto done;
+        for (int i = 0; i < num_want; i++)
+        {
+            if (!out_node_name[want_ids[i]]) goto done;
+            names[i] = out_node_name[want_ids[i]];
+        }
+        if (set_graph_output_node(graph, names, num_want) < 0) goto done;
+        free(names);
+    }
+
+    struct options opt;
+    opt.num_thread = num_thread;
+    opt.cluster = TENGINE_CLUSTER_ALL;
+    opt.precision = precision;
+    opt.affinity = 0;
+    if (prerun_graph_multithread(graph, opt) < 0)
+    {
+        fprintf(stderr, "ref_shim: prerun failed\n");
+        rc = -103;
+        goto done;
+    }
+    /* the shapes the reference inferred must be the shapes the caller described */
+    for (int i = 0; i < num_tensors; i++)
+    {
+        if (!tt[i]) continue;
+        int dims[8] = {0};
+        int nd = get_tensor_shape(tt[i], dims, 8);
+        int64_t a = 1, b = 1;
+        for (int k = 0; k < nd; k++) a *= dims[k];
+        for (int k = 0; k < 4; k++) b *= tensors[i].dims[k];
+        if (a != b)
+        {
+            fprintf(stderr, "ref_shim: tensor %d shape mismatch: reference inferred %d dims [%d %d %d %d]\n", i, nd,
+                    dims[0], dims[1], dims[2], dims[3]);
+            rc = -104;
+            goto done_postrun;
+        }
+    }
+    for (int i = 0; i < num_inputs; i++)
+    {
+        const tb200_tensor_desc* d = &tensors[input_ids[i]];
+        int bytes = d->dims[0] * d->dims[1] * d->dims[2] * d->dims[3];
+        if (set_tensor_buffer(tt[input_ids[i]], (void*)in_bufs[i], bytes) < 0) goto done_postrun;
+    }
+    for (int i = 0; i < warmup; i++)
+        if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
+    {
+        double mn = 1e30, sum = 0;
+        for (int i = 0; i < loops; i++)
+        {
+            double t0 = now_ms();
+            if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
+            double dt = now_ms() - t0;
+            if (dt < mn) mn = dt;
+            sum += dt;
+        }
+        if (ms_stats) ms_stats[0] = mn, ms_stats[1] = loops ? sum / loops : 0;
+    }
+    for (int i = 0; i < num_want; i++)
+    {
+        const tb200_tensor_desc* d = &tensors[want_ids[i]];
+        size_t bytes = (size_t)d->dims[0] * d->dims[1] * d->dims[2] * d->dims[3];
+        void* p = get_tensor_buffer(tt[want_ids[i]]);
+        if (!p) { rc = -106; goto done_postrun; }
+        if (p != out_bufs[i]) memcpy(out_bufs[i], p, bytes);
+    }
+    rc = 0;
+done_postrun:
+    postrun_graph(graph);
+done:
+    destroy_graph(graph);
+    if (ctx) destroy_context(ctx);
+    for (int i = 0; i < num_tensors; i++) free(out_node_name[i]);
+    free(out_node_name);
+    free(tt);
+    return rc;
+}
+
+SHIM_API const char* ref_shim_version(void) { return get_tengine_version(); }

@@ -1,0 +1,126 @@
+// common.cuh -- device-side numerics shared by every kernel of the B200 backend.
+//
+// The requantising epilogue reproduces the reference CPU device's float arithmetic operation for
+// operation (no FMA contraction, IEEE division, C round() = half away from zero), so that int8 results are
+// bit-identical to the reference and uint8 results differ only by the reference's own fp32 summation noise.
+// Reference recipes (paths relative to source/device/cpu/op/):
+//   HCL int8  : conv/x86/conv_kernel_x86.c:1827-1889, conv/x86/conv_dw_hcl_x86.c:198-262
+//   REF int8  : conv/conv_kernel_ref_int8.c:136-171
+//   HCL uint8 : conv/x86/conv_kernel_x86.c:1729-1791
+//   REF uint8 : conv/conv_kernel_ref_uint8.c:157-186
+//   FC int8   : fc/fc_ref.c:225,252      FC uint8 : fc/fc_ref.c:146-166
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tengine_b200.h"
+
+namespace tb200 {
+
+// Scalar epilogue parameters, passed by value to kernels (per-channel arrays stay in global memory).
+struct EpiParams
+{
+    const int32_t* bias;  // [OCp]
+    const float* w_scale; // [OCp]
+    float in_scale, out_scale;
+    float in_w_scale;     // uint8: s_in * s_w (per tensor), computed once on the host in fp32
+    int32_t in_zero, w_zero, out_zero;
+    int32_t activation;
+    int32_t recipe;
+    int32_t is_uint8;
+    int32_t fc_rounding;
+    int32_t has_bias;
+};
+
+// C round(): half away from zero, exact for every float (CUDA's roundf is the exact, slow-path version).
+__device__ __forceinline__ float round_half_away(float x) { return roundf(x); }
+
+__device__ __forceinline__ float act_hcl(float f, int activation)
+{
+    if (activation == 0) f = (f < 0.f) ? 0.f : f;
+    if (activation > 0)
+    {
+        f = (f < 0.f) ? 0.f : f;
+        f = (f > 6.f) ? 6.f : f;
+    }
+    return f;
+}
+
+__device__ __forceinline__ float act_ref(float t, int activation)
+{
+    if (activation >= 0)
+    {
+        if (t < 0.f && activation != 1) t = 0.f;
+        if (t > 1.f && activation == 1) t = 1.f;
+        if (t > 6.f && activation == 6) t = 6.f;
+        if (t < -1.f && activation == 1) t = -1.f;
+    }
+    return t;
+}
+
+// acc = exact integer dot product (int8: sum x*w; uint8: sum (x-zx)(w-zw) over in-bounds taps), WITHOUT bias.
+// Returns the output byte (int8 bit pattern or uint8).
+__device__ __forceinline__ int requant(int32_t acc, int oc, const EpiParams& e)
+{
+    const int32_t b = e.has_bias ? __ldg(e.bias + oc) : 0;
+    if (!e.is_uint8)
+    {
+        const float s_w = __ldg(e.w_scale + oc);
+        int q;
+        if (e.fc_rounding)
+        {
+            // fc_ref.c:225 requant = (s_in*s_w)/s_out ; :252 roundf(acc_with_bias * requant)
+            const float rq = __fdiv_rn(__fmul_rn(e.in_scale, s_w), e.out_scale);
+            q = (int)roundf(__fmul_rn((float)(acc + b), rq));
+        }
+        else if (e.recipe == TB200_RECIPE_HCL)
+        {
+            float f = __fmul_rn(__fmul_rn((float)(acc + b), e.in_scale), s_w);
+            f = act_hcl(f, e.activation);
+            q = (int)round_half_away(__fdiv_rn(f, e.out_scale));
+        }
+        else
+        {
+            float f = __fmul_rn((float)(acc + b), __fmul_rn(e.in_scale, s_w));
+            f = act_ref(f, e.activation);
+            q = (int)round_half_away(__fdiv_rn(f, e.out_scale));
+        }
+        q = q > 127 ? 127 : q;
+        q = q < -127 ? -127 : q;
+        return q & 0xff;
+    }
+    else
+    {
+        float f = __fmul_rn((float)acc, e.in_w_scale);
+        int q;
+        if (e.fc_rounding)
+        {
+            // fc_ref.c:146,162: data = bias*bias_scale + sum ; roundf(data / s_out) + zp  (bias_scale == s_in*s_w)
+            if (e.has_bias) f = __fadd_rn(f, __fmul_rn((float)b, e.in_w_scale));
+            q = (int)roundf(__fdiv_rn(f, e.out_scale)) + e.out_zero;
+        }
+        else
+        {
+            if (e.has_bias)
+            {
+                // conv_kernel_x86.c:1723,1740: bias * (s_in*s_w) ; conv_kernel_ref_uint8.c:94: (bias * s_in) * s_w
+                const float bt = (e.recipe == TB200_RECIPE_HCL)
+                                     ? __fmul_rn((float)b, e.in_w_scale)
+                                     : __fmul_rn(__fmul_rn((float)b, e.in_scale), __ldg(e.w_scale + oc));
+                f = __fadd_rn(f, bt);
+            }
+            f = (e.recipe == TB200_RECIPE_HCL) ? act_hcl(f, e.activation) : act_ref(f, e.activation);
+            q = (int)round_half_away(__fdiv_rn(f, e.out_scale)) + e.out_zero;
+        }
+        q = q > 255 ? 255 : q;
+        q = q < 0 ? 0 : q;
+        return q;
+    }
+}
+
+__device__ __forceinline__ int dp4a_s8(int a, int b, int c) { return __dp4a(a, b, c); }
+__device__ __forceinline__ unsigned dp4a_u8(unsigned a, unsigned b, unsigned c) { return __dp4a(a, b, c); }
+
+static inline int cpad(int c) { return (c + 15) & ~15; }
+
+} // namespace tb200

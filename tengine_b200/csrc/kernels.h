@@ -1,0 +1,67 @@
+// kernels.h -- internal launcher interface between the graph executor (engine.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace tb200 {
+
+struct ConvShape
+{
+    int n, h, w, c, cp;  // input: logical channels c, padded pitch cp
+    int cg, cgp;         // channels per group (logical) and per-group pitch of the weight layout
+    int oh, ow, oc, ocp; // output
+    int kh, kw, sh, sw, ph0, pw0, dh, dw, group;
+};
+
+struct PoolShape
+{
+    int n, h, w, c, cp, oh, ow;
+    int kh, kw, sh, sw, ph0, pw0;
+    int method, caffe_flavor;
+    float in_scale, out_scale;
+    int in_zero, out_zero;
+};
+
+struct PointwiseParams
+{
+    int mode; // 0 relu / leaky relu, 1 sum, 2 prod
+    int c, cp;
+    float scale0, scale1, out_scale;
+    int zero0, zero1, out_zero;
+    float negative_slope;
+};
+
+cudaError_t launch_conv_direct(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st);
+cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long bytes, const PointwiseParams& p, bool u8, cudaStream_t st);
+cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+                               int z_in, float s_out, int z_out, bool u8, cudaStream_t st);
+cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st);
+cudaError_t launch_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
+cudaError_t launch_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
+
+// ---- tcgen05 GEMM (gemm_tcgen05.cu) ------------------------------------------------------------------
+// out[M][ldo] (bytes) = requant( A[M][K] (row pitch lda bytes) . B[OCp][K]^T )
+struct GemmPlan
+{
+    alignas(64) unsigned char tmap_a[128]; // CUtensorMap
+    alignas(64) unsigned char tmap_b[128];
+    long long m;
+    int k;       // padded K (multiple of 16)
+    int oc, ocp; // logical / padded output channels
+    int ldo;     // output row pitch in bytes
+    int block_n, block_k, stages, k_blocks, n_tiles;
+    long long m_tiles;
+    int swizzle; // 32 / 64 / 128
+    int variant; // debug: descriptor variant selector (0 = default)
+};
+// Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
+int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
+                     int variant);
+cudaError_t launch_gemm_i8(const GemmPlan& plan, void* out, const EpiParams& e, int num_sms, cudaStream_t st);
+
+} // namespace tb200

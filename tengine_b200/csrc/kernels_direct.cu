@@ -1,0 +1,552 @@
+// kernels_direct.cu -- CUDA-core (dp4a) kernels of the B200 backend: generic direct convolution, depthwise,
+// NCHW stem, and the HBM-bound glue ops (pool / relu / eltwise / concat / upsample / layout).
+//
+// Device layout: activations NHWC, channels padded to a multiple of 16 (pad lanes hold 0), 1 byte/element.
+// These kernels are the general path (any kernel/stride/pad/dilation/group) and the on-device cross-check
+// for the tcgen05 GEMM path; the dense 1x1 / FC contractions run in gemm_tcgen05.cu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tb200 {
+
+// ------------------------------------------------------------------------------------------------------
+// Generic direct convolution.  Thread = one output pixel x OCT consecutive output channels.
+// Weights [OCp][KH][KW][CGp] (CGp = padded channels per group, multiple of 16 when group == 1,
+// multiple of 4 otherwise).  Takes the role of ref_conv_int8 / ref_conv_uint8 (conv_kernel_ref_*.c) and of
+// im2col+sgemm for shapes the tensor-core path does not cover.
+// ------------------------------------------------------------------------------------------------------
+template <bool U8, int OCT>
+__global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
+                                                          uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+{
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)s.n * s.oh * s.ow;
+    if (pix >= npix) return;
+    const int oc0 = blockIdx.y * OCT;
+    const int ow = (int)(pix % s.ow);
+    const int oh = (int)((pix / s.ow) % s.oh);
+    const int n = (int)(pix / ((long long)s.ow * s.oh));
+    const int og = s.oc / s.group;              // logical out channels per group
+    const int g = (oc0 < s.oc) ? oc0 / og : 0;  // OCT divides og or group == 1 (host guarantees)
+    const int cin0 = g * s.cg;                  // first logical input channel of the group
+    const int words = s.cgp / 4;
+
+    int acc[OCT];
+    int sw_sum[OCT]; // uint8: sum of weights over in-bounds taps
+#pragma unroll
+    for (int j = 0; j < OCT; j++) acc[j] = 0, sw_sum[j] = 0;
+    int sx_sum = 0, taps = 0;
+
+    for (int kh = 0; kh < s.kh; kh++)
+    {
+        const int iy = oh * s.sh - s.ph0 + kh * s.dh;
+        if (iy < 0 || iy >= s.h) continue;
+        for (int kw = 0; kw < s.kw; kw++)
+        {
+            const int ix = ow * s.sw - s.pw0 + kw * s.dw;
+            if (ix < 0 || ix >= s.w) continue;
+            taps++;
+            const int* xp = reinterpret_cast<const int*>(in + (((size_t)n * s.h + iy) * s.w + ix) * s.cp + cin0);
+            const int* wp = reinterpret_cast<const int*>(wgt + ((size_t)oc0 * s.kh * s.kw + (size_t)kh * s.kw + kw) * s.cgp);
+            const size_t wstride = (size_t)s.kh * s.kw * words; // ints between consecutive output channels
+            for (int c = 0; c < words; c++)
+            {
+                const int xv = __ldg(xp + c);
+                if (U8) sx_sum = (int)dp4a_u8((unsigned)xv, 0x01010101u, (unsigned)sx_sum);
+#pragma unroll
+                for (int j = 0; j < OCT; j++)
+                {
+                    const int wv = __ldg(wp + j * wstride + c);
+                    if (U8)
+                    {
+                        acc[j] = (int)dp4a_u8((unsigned)xv, (unsigned)wv, (unsigned)acc[j]);
+                        sw_sum[j] = (int)dp4a_u8((unsigned)wv, 0x01010101u, (unsigned)sw_sum[j]);
+                    }
+                    else
+                        acc[j] = dp4a_s8(xv, wv, acc[j]);
+                }
+            }
+        }
+    }
+
+    uint8_t* op = out + (size_t)pix * s.ocp + oc0;
+#pragma unroll
+    for (int j = 0; j < OCT; j += 4)
+    {
+        unsigned packed = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+        {
+            const int oc = oc0 + j + t;
+            int q = 0;
+            if (oc < s.oc)
+            {
+                int a = acc[j + t];
+                if (U8) // sum (x-zx)(w-zw) = Sxw - zw*Sx - zx*Sw + cnt*zx*zw   (cnt counts REAL channels only)
+                    a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.cg * e.in_zero * e.w_zero;
+                q = requant(a, oc, e);
+            }
+            packed |= (unsigned)q << (8 * t);
+        }
+        *reinterpret_cast<unsigned*>(op + j) = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Depthwise convolution (group == C == OC), any kernel size.  Thread = one output pixel x 4 channels.
+// Weights [KH][KW][Cp].  Takes the role of convdw3x3s{1,2}_int8_sse (conv_dw_hcl_x86.c:97-445) and of
+// ref_conv_* for the depthwise cases the reference sends to conv_ref (batch > 1, uint8).
+// ------------------------------------------------------------------------------------------------------
+template <bool U8>
+__global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
+                                                      uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+{
+    const int cw = s.cp / 4; // channel words per pixel
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)s.n * s.oh * s.ow * cw;
+    if (idx >= total) return;
+    const int c4 = (int)(idx % cw);
+    const long long pix = idx / cw;
+    const int ow = (int)(pix % s.ow);
+    const int oh = (int)((pix / s.ow) % s.oh);
+    const int n = (int)(pix / ((long long)s.ow * s.oh));
+
+    int acc[4] = {0, 0, 0, 0};
+    for (int kh = 0; kh < s.kh; kh++)
+    {
+        const int iy = oh * s.sh - s.ph0 + kh * s.dh;
+        if (iy < 0 || iy >= s.h) continue;
+        for (int kw = 0; kw < s.kw; kw++)
+        {
+            const int ix = ow * s.sw - s.pw0 + kw * s.dw;
+            if (ix < 0 || ix >= s.w) continue;
+            const unsigned xv = __ldg(reinterpret_cast<const unsigned*>(in + (((size_t)n * s.h + iy) * s.w + ix) * s.cp) + c4);
+            const unsigned wv = __ldg(reinterpret_cast<const unsigned*>(wgt + ((size_t)kh * s.kw + kw) * s.cp) + c4);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+            {
+                int xb, wb;
+                if (U8)
+                {
+                    xb = (int)((xv >> (8 * t)) & 0xff) - e.in_zero;
+                    wb = (int)((wv >> (8 * t)) & 0xff) - e.w_zero;
+                }
+                else
+                {
+                    xb = (int)(int8_t)(xv >> (8 * t));
+                    wb = (int)(int8_t)(wv >> (8 * t));
+                }
+                acc[t] += xb * wb;
+            }
+        }
+    }
+    unsigned packed = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+    {
+        const int c = c4 * 4 + t;
+        const int q = (c < s.oc) ? requant(acc[t], c, e) : 0;
+        packed |= (unsigned)q << (8 * t);
+    }
+    reinterpret_cast<unsigned*>(out + (size_t)pix * s.ocp)[c4] = packed;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stem: NCHW input with C <= 4 (the network input as the application hands it over) -> NHWC output.
+// Thread = one output pixel x OCT output channels.  Weights [OCp][KH][KW][4].
+// Fuses the NCHW->NHWC conversion of the graph input into the first convolution.
+// ------------------------------------------------------------------------------------------------------
+template <bool U8, int OCT>
+__global__ void __launch_bounds__(128) conv_stem_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
+                                                        uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+{
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)s.n * s.oh * s.ow;
+    if (pix >= npix) return;
+    const int oc0 = blockIdx.y * OCT;
+    const int ow = (int)(pix % s.ow);
+    const int oh = (int)((pix / s.ow) % s.oh);
+    const int n = (int)(pix / ((long long)s.ow * s.oh));
+    const size_t plane = (size_t)s.h * s.w;
+    const uint8_t* img = in + (size_t)n * s.c * plane;
+
+    int acc[OCT];
+    int sw_sum[OCT];
+#pragma unroll
+    for (int j = 0; j < OCT; j++) acc[j] = 0, sw_sum[j] = 0;
+    int sx_sum = 0, taps = 0;
+
+    for (int kh = 0; kh < s.kh; kh++)
+    {
+        const int iy = oh * s.sh - s.ph0 + kh * s.dh;
+        if (iy < 0 || iy >= s.h) continue;
+        for (int kw = 0; kw < s.kw; kw++)
+        {
+            const int ix = ow * s.sw - s.pw0 + kw * s.dw;
+            if (ix < 0 || ix >= s.w) continue;
+            taps++;
+            unsigned xv = 0;
+            for (int c = 0; c < s.c; c++) xv |= (unsigned)__ldg(img + c * plane + (size_t)iy * s.w + ix) << (8 * c);
+            if (U8) sx_sum = (int)dp4a_u8(xv, 0x01010101u, (unsigned)sx_sum);
+            const int* wp = reinterpret_cast<const int*>(wgt) + ((size_t)oc0 * s.kh + kh) * s.kw + kw;
+#pragma unroll
+            for (int j = 0; j < OCT; j++)
+            {
+                const int wv = __ldg(wp + (size_t)j * s.kh * s.kw);
+                if (U8)
+                {
+                    acc[j] = (int)dp4a_u8(xv, (unsigned)wv, (unsigned)acc[j]);
+                    sw_sum[j] = (int)dp4a_u8((unsigned)wv, 0x01010101u, (unsigned)sw_sum[j]);
+                }
+                else
+                    acc[j] = dp4a_s8((int)xv, wv, acc[j]);
+            }
+        }
+    }
+    uint8_t* op = out + (size_t)pix * s.ocp + oc0;
+#pragma unroll
+    for (int j = 0; j < OCT; j += 4)
+    {
+        unsigned packed = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+        {
+            const int oc = oc0 + j + t;
+            int q = 0;
+            if (oc < s.oc)
+            {
+                int a = acc[j + t];
+                if (U8) a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.c * e.in_zero * e.w_zero;
+                q = requant(a, oc, e);
+            }
+            packed |= (unsigned)q << (8 * t);
+        }
+        *reinterpret_cast<unsigned*>(op + j) = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Glue ops.  All follow the reference's dequant -> fp32 op -> requant arithmetic literally.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clamp_i8(int q) { return (q > 127 ? 127 : (q < -127 ? -127 : q)) & 0xff; }
+__device__ __forceinline__ int clamp_u8(int q) { return q > 255 ? 255 : (q < 0 ? 0 : q); }
+
+// pooling/pooling_kernel_ref_int8.c:84-189, pooling_kernel_ref_uint8.c:91-204. Thread = pixel x 4 channels.
+template <bool U8>
+__global__ void __launch_bounds__(256) pool_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, PoolShape p)
+{
+    const int cw = p.cp / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.n * p.oh * p.ow * cw;
+    if (idx >= total) return;
+    const int c4 = (int)(idx % cw);
+    const long long pix = idx / cw;
+    const int pw = (int)(pix % p.ow);
+    const int ph = (int)((pix / p.ow) % p.oh);
+    const int n = (int)(pix / ((long long)p.ow * p.oh));
+
+    int h_start = ph * p.sh - p.ph0, h_end = h_start + p.kh;
+    if (h_end > p.h + p.ph0) h_end = p.h + p.ph0;
+    int w_start = pw * p.sw - p.pw0, w_end = w_start + p.kw;
+    if (w_end > p.w + p.pw0) w_end = p.w + p.pw0;
+    int pool_size = 1;
+    if (p.caffe_flavor) pool_size = (h_end - h_start) * (w_end - w_start);
+    h_start = h_start > 0 ? h_start : 0;
+    w_start = w_start > 0 ? w_start : 0;
+    h_end = h_end < p.h ? h_end : p.h;
+    w_end = w_end < p.w ? w_end : p.w;
+    if (!p.caffe_flavor) pool_size = (h_end - h_start) * (w_end - w_start);
+
+    int isum[4] = {0, 0, 0, 0};
+    int imax[4];
+    float fsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float fmax[4];
+    bool first = true;
+    for (int i = h_start; i < h_end; i++)
+        for (int j = w_start; j < w_end; j++)
+        {
+            const unsigned xv = __ldg(reinterpret_cast<const unsigned*>(in + (((size_t)n * p.h + i) * p.w + j) * p.cp) + c4);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+            {
+                if (U8)
+                {
+                    // dequantise first, then max / sum in fp32 (pooling_kernel_ref_uint8.c:131-133)
+                    const float f = __fmul_rn((float)((int)((xv >> (8 * t)) & 0xff) - p.in_zero), p.in_scale);
+                    fmax[t] = first ? f : (fmax[t] > f ? fmax[t] : f);
+                    fsum[t] = __fadd_rn(fsum[t], f);
+                }
+                else
+                {
+                    const int v = (int)(int8_t)(xv >> (8 * t));
+                    imax[t] = first ? v : (imax[t] > v ? imax[t] : v);
+                    isum[t] += v;
+                }
+            }
+            first = false;
+        }
+    unsigned packed = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+    {
+        int q = 0;
+        if (c4 * 4 + t < p.c)
+        {
+            if (U8)
+            {
+                const float v = (p.method == TB200_POOL_MAX) ? fmax[t] : __fdiv_rn(fsum[t], (float)pool_size);
+                q = (int)roundf(__fdiv_rn(v, p.out_scale)) + p.out_zero;
+                q = (q > 255 ? 255 : q) & 0xff; // pooling_kernel_ref_uint8.c:197: upper clamp only
+            }
+            else if (p.method == TB200_POOL_MAX)
+                q = clamp_i8((int)roundf(__fmul_rn((float)imax[t], __fdiv_rn(p.in_scale, p.out_scale))));
+            else
+            {
+                float f = __fmul_rn((float)isum[t], p.in_scale);
+                f = __fdiv_rn(f, (float)pool_size);
+                q = clamp_i8((int)roundf(__fdiv_rn(f, p.out_scale)));
+            }
+        }
+        packed |= (unsigned)q << (8 * t);
+    }
+    reinterpret_cast<unsigned*>(out + (size_t)pix * p.cp)[c4] = packed;
+}
+
+// relu/relu_kernel_ref_int8.c:41-94, relu_kernel_ref_uint8.c:41-96; eltwise/eltwise_ref.c:311-583,585-845.
+// One thread = 16 bytes.  mode 0: relu(a); 1: a+b; 2: a*b.  Pad lanes: int8 0 -> 0; uint8 handled by `c` mask.
+template <bool U8>
+__global__ void __launch_bounds__(256) pointwise_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                        uint4* __restrict__ out, long long nvec, PointwiseParams p)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 va = __ldg(a + i);
+    uint4 vb = make_uint4(0, 0, 0, 0);
+    if (p.mode != 0) vb = __ldg(b + i);
+    const unsigned wa[4] = {va.x, va.y, va.z, va.w};
+    const unsigned wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    unsigned wo[4];
+    const int lane0 = (int)((i * 16) % p.cp); // channel index of byte 0 of this vector
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+    {
+        unsigned packed = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+        {
+            const int ch = lane0 + w * 4 + t;
+            int q = 0;
+            if (ch < p.c)
+            {
+                float f0, f1 = 0.f;
+                if (U8)
+                {
+                    f0 = __fmul_rn((float)((int)((wa[w] >> (8 * t)) & 0xff) - p.zero0), p.scale0);
+                    f1 = __fmul_rn((float)((int)((wb[w] >> (8 * t)) & 0xff) - p.zero1), p.scale1);
+                }
+                else
+                {
+                    f0 = __fmul_rn((float)(int)(int8_t)(wa[w] >> (8 * t)), p.scale0);
+                    f1 = __fmul_rn((float)(int)(int8_t)(wb[w] >> (8 * t)), p.scale1);
+                }
+                float f;
+                if (p.mode == 0)
+                    f = (f0 < 0.f) ? ((p.negative_slope == 0.f) ? 0.f : __fmul_rn(f0, p.negative_slope)) : f0;
+                else if (p.mode == 1)
+                    f = __fadd_rn(f0, f1);
+                else
+                    f = __fmul_rn(f0, f1);
+                if (U8)
+                {
+                    if (p.mode == 0) // relu_kernel_ref_uint8.c:85 round(f/s + zp): zero point added INSIDE round
+                        q = clamp_u8((int)roundf(__fadd_rn(__fdiv_rn(f, p.out_scale), (float)p.out_zero)));
+                    else
+                        q = clamp_u8((int)roundf(__fdiv_rn(f, p.out_scale)) + p.out_zero);
+                }
+                else
+                    q = clamp_i8((int)roundf(__fdiv_rn(f, p.out_scale)));
+            }
+            packed |= (unsigned)q << (8 * t);
+        }
+        wo[w] = packed;
+    }
+    out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+}
+
+// concat along channels with per-input requantisation (concat_kernel_ref_int8.c:70-80 roundf(q*s_in/s_out),
+// concat_kernel_ref_uint8.c dequant/requant), and nearest upsample (upsample_ref.c:74); one byte per thread
+// (channel counts such as 255 / 384 need not be multiples of 4 at the seams).
+template <bool U8>
+__global__ void __launch_bounds__(256) concat_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                     long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+                                                     int z_in, float s_out, int z_out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * c) return;
+    const int ch = (int)(idx % c);
+    const long long pix = idx / c;
+    const uint8_t v = in[pix * cp_in + ch];
+    int q;
+    if (U8)
+    {
+        const float f = __fmul_rn((float)v - (float)z_in, s_in);
+        q = clamp_u8((int)roundf(__fdiv_rn(f, s_out)) + z_out);
+    }
+    else
+    {
+        q = (int)roundf(__fmul_rn((float)(int)(int8_t)v, __fdiv_rn(s_in, s_out)));
+        q = (q > 127 ? 127 : (q < -127 ? 127 : q)) & 0xff; // sic: concat_kernel_ref_int8.c:77-78
+    }
+    out[pix * cp_out + c_off + ch] = (uint8_t)q;
+}
+
+__global__ void __launch_bounds__(256) upsample_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int h,
+                                                       int w, int cvec, int scale)
+{
+    const int oh = h * scale, ow = w * scale;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * oh * ow * cvec;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvec);
+    const long long pix = idx / cvec;
+    const int x = (int)(pix % ow), y = (int)((pix / ow) % oh), b = (int)(pix / ((long long)ow * oh));
+    out[idx] = __ldg(in + (((size_t)b * h + y / scale) * w + x / scale) * cvec + cv);
+}
+
+// host NCHW <-> device NHWC(pad).  32x32 byte tile transposes through shared memory: coalesced both ways.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int c,
+                                                           int hw, int cp)
+{
+    __shared__ uint8_t tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    for (int r = ty; r < 32; r += 8)
+    {
+        const int ch = c0 + r, p = hw0 + tx;
+        tile[r][tx] = (ch < c && p < hw) ? in[((size_t)n * c + ch) * hw + p] : 0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+    {
+        const int p = hw0 + r, ch = c0 + tx;
+        if (p < hw && ch < cp) out[((size_t)n * hw + p) * cp + ch] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int c,
+                                                           int hw, int cp)
+{
+    __shared__ uint8_t tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+    {
+        const int p = hw0 + r, ch = c0 + tx;
+        tile[r][tx] = (p < hw && ch < cp) ? in[((size_t)n * hw + p) * cp + ch] : 0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+    {
+        const int ch = c0 + r, p = hw0 + tx;
+        if (ch < c && p < hw) out[((size_t)n * c + ch) * hw + p] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+cudaError_t launch_conv_direct(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+{
+    const long long npix = (long long)s.n * s.oh * s.ow;
+    const int og = s.oc / s.group;
+    // OCT output channels per thread; with groups every tile must stay inside one group
+    int oct = 8;
+    if (s.group > 1 && (og % 8) != 0) oct = 4;
+    if (s.group > 1 && (og % 4) != 0) return cudaErrorInvalidValue;
+    dim3 grid(blocks_for(npix, 128), (s.ocp + oct - 1) / oct);
+    const uint8_t* i8 = (const uint8_t*)in;
+    const uint8_t* w8 = (const uint8_t*)w;
+    uint8_t* o8 = (uint8_t*)out;
+    if (e.is_uint8)
+    {
+        if (oct == 8) conv_direct_kernel<true, 8><<<grid, 128, 0, st>>>(i8, w8, o8, s, e);
+        else conv_direct_kernel<true, 4><<<grid, 128, 0, st>>>(i8, w8, o8, s, e);
+    }
+    else
+    {
+        if (oct == 8) conv_direct_kernel<false, 8><<<grid, 128, 0, st>>>(i8, w8, o8, s, e);
+        else conv_direct_kernel<false, 4><<<grid, 128, 0, st>>>(i8, w8, o8, s, e);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+{
+    const long long total = (long long)s.n * s.oh * s.ow * (s.cp / 4);
+    if (e.is_uint8) conv_dw_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    else conv_dw_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+{
+    const long long npix = (long long)s.n * s.oh * s.ow;
+    dim3 grid(blocks_for(npix, 128), s.ocp / 16);
+    if (e.is_uint8) conv_stem_kernel<true, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    else conv_stem_kernel<false, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st)
+{
+    const long long total = (long long)p.n * p.oh * p.ow * (p.cp / 4);
+    if (u8) pool_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
+    else pool_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long bytes, const PointwiseParams& p, bool u8, cudaStream_t st)
+{
+    const long long nvec = bytes / 16;
+    if (u8) pointwise_kernel<true><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
+    else pointwise_kernel<false><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+                               int z_in, float s_out, int z_out, bool u8, cudaStream_t st)
+{
+    const long long total = npix * c;
+    if (u8) concat_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
+    else concat_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st)
+{
+    const long long total = (long long)n * h * scale * w * scale * (cp / 16);
+    upsample_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, n, h, w, cp / 16, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st)
+{
+    const int hw = h * w, cp = cpad(c);
+    dim3 grid((hw + 31) / 32, (cp + 31) / 32, n);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, c, hw, cp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st)
+{
+    const int hw = h * w, cp = cpad(c);
+    dim3 grid((hw + 31) / 32, (cp + 31) / 32, n);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, c, hw, cp);
+    return cudaGetLastError();
+}
+
+} // namespace tb200

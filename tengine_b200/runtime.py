@@ -1,0 +1,174 @@
+"""ctypes binding of libtengine_b200.so (the C ABI in include/tengine_b200.h) for tests and bench.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtengine_b200.so")
+_lib = None
+
+
+class TB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tb200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile tengine_b200/csrc for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libtengine_b200.so failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    if verbose:
+        print(r.stdout[-1500:])
+
+
+def lib():
+    """Load the library; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the B200 backend has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.tb200_last_error.restype = C.c_char_p
+        L.tb200_graph_layer_kernel.restype = C.c_char_p
+        L.tb200_context_stream.restype = C.c_void_p
+        L.tb200_host_alloc.restype = C.c_void_p
+        L.tb200_host_alloc.argtypes = [C.c_size_t]
+        L.tb200_host_free.argtypes = [C.c_void_p]
+        L.tb200_graph_layer_kernel.argtypes = [C.c_void_p, C.c_int]
+        for name in ("tb200_graph_run", "tb200_graph_upload", "tb200_graph_launch", "tb200_graph_download",
+                     "tb200_graph_sync", "tb200_graph_postrun", "tb200_graph_weight_arena",
+                     "tb200_graph_num_launches", "tb200_graph_read_tensor", "tb200_graph_profile",
+                     "tb200_graph_work", "tb200_context_destroy"):
+            getattr(L, name).restype = C.c_int
+        L.tb200_graph_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.tb200_graph_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.tb200_graph_launch.argtypes = [C.c_void_p]
+        L.tb200_graph_sync.argtypes = [C.c_void_p]
+        L.tb200_graph_postrun.argtypes = [C.c_void_p]
+        L.tb200_graph_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb200_graph_read_tensor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.tb200_graph_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.tb200_graph_work.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb200_graph_weight_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb200_graph_num_launches.argtypes = [C.c_void_p]
+        L.tb200_context_destroy.argtypes = [C.c_void_p]
+        L.tb200_context_stream.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise TB200Error(rc, lib().tb200_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return lib().tb200_device_count()
+
+
+class Context:
+    """interface->init / release_device: binds one GPU."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().tb200_context_create(int(device), C.byref(self.h)))
+        self.device = device
+
+    @property
+    def stream(self):
+        return lib().tb200_context_stream(self.h)
+
+    def close(self):
+        if self.h:
+            lib().tb200_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class PinnedBuffer:
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().tb200_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("tb200_host_alloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().tb200_host_free(self.ptr)
+            self.ptr = None
+
+
+class Graph:
+    """tb200_graph_prerun / run / postrun over a GraphDef (device->interface pre_run/run/post_run)."""
+
+    def __init__(self, ctx, gdef, flags=abi.PRERUN_DEFAULT):
+        self.ctx, self.gdef = ctx, gdef
+        T, L = gdef.c_tables()
+        self.h = C.c_void_p()
+        _check(lib().tb200_graph_prerun(ctx.h, T, len(gdef.tensors), L, len(gdef.layers), gdef.id_array(gdef.inputs),
+                                        len(gdef.inputs), gdef.id_array(gdef.outputs), len(gdef.outputs), int(flags),
+                                        C.byref(self.h)))
+
+    def run(self, inputs, outputs=None):
+        g = self.gdef
+        ins = [np.ascontiguousarray(x) for x in inputs]
+        for x, t in zip(ins, g.inputs):
+            assert x.shape == g.dims(t) and x.dtype == g.np_dtype, (x.shape, g.dims(t), x.dtype)
+        if outputs is None:
+            outputs = [np.empty(g.dims(t), dtype=g.np_dtype) for t in g.outputs]
+        ip = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+        op = (C.c_void_p * len(outputs))(*[a.ctypes.data for a in outputs])
+        _check(lib().tb200_graph_run(self.h, ip, op))
+        return outputs
+
+    def upload(self, i, x):
+        _check(lib().tb200_graph_upload(self.h, i, x.ctypes.data))
+
+    def launch(self):
+        _check(lib().tb200_graph_launch(self.h))
+
+    def download(self, i, out):
+        _check(lib().tb200_graph_download(self.h, i, out.ctypes.data))
+
+    def sync(self):
+        _check(lib().tb200_graph_sync(self.h))
+
+    def read_tensor(self, t):
+        out = np.empty(self.gdef.dims(t), dtype=self.gdef.np_dtype)
+        _check(lib().tb200_graph_read_tensor(self.h, t, out.ctypes.data))
+        return out
+
+    def layer_kernels(self):
+        return [lib().tb200_graph_layer_kernel(self.h, i).decode() for i in range(len(self.gdef.layers))]
+
+    def num_launches(self):
+        return lib().tb200_graph_num_launches(self.h)
+
+    def profile(self):
+        ms = (C.c_float * len(self.gdef.layers))()
+        _check(lib().tb200_graph_profile(self.h, ms, len(self.gdef.layers)))
+        return list(ms)
+
+    def work(self):
+        ops, byts = C.c_double(), C.c_double()
+        _check(lib().tb200_graph_work(self.h, C.byref(ops), C.byref(byts)))
+        return ops.value, byts.value
+
+    def weight_arena(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().tb200_graph_weight_arena(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if self.h:
+            lib().tb200_graph_postrun(self.h)
+            self.h = C.c_void_p()

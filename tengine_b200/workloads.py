@@ -1,0 +1,214 @@
+"""Synthetic quantised workloads of BASELINE.json: MobileNet-v1, ResNet-50, YOLOv3-tiny as GraphDef tables.
+
+Layer shapes follow the reference's own benchmark/models/{mobilenet,resnet50,yolov3_tiny}_benchmark.tmfile
+(SURVEY.md 8(a) layer tables).  Weights are seeded random (there is no network for checkpoints); they are
+quantised the way the reference's tools/quantize/quant_save_graph.cpp does it:
+  int8  : symmetric per-output-channel weight scales max|w|/127 (:519-555), activations per tensor max|a|/127
+  uint8 : asymmetric per-tensor (scale, zero_point) for weights and activations (:246-263)
+  bias  : int32 with scale s_in*s_w[oc] (:579-600, :283-298)
+Activation scales come from one fp32 calibration pass (torch CPU) over a small seeded batch, so that the
+quantised activations neither saturate nor collapse.
+Test/bench infrastructure; not part of the device library.
+"""
+import numpy as np
+
+from . import abi
+from .graphdef import GraphDef
+
+
+class _H:  # handle: tensor id + fp32 calibration activation
+    def __init__(self, tid, act):
+        self.tid, self.act = tid, act
+
+
+class QuantBuilder:
+    def __init__(self, data_type, batch, c, h, w, seed=1234, calib_batch=2):
+        import torch
+
+        self.torch = torch
+        self.g = GraphDef(data_type)
+        self.u8 = data_type == abi.DT_UINT8
+        self.rng = np.random.default_rng(seed)
+        self.batch = batch
+        # network input: int8 in [-127,127] with scale 1/127; uint8 in [0,255] with scale 2/255, zp 128
+        if self.u8:
+            self.in_scale, self.in_zero = np.float32(2.0 / 255.0), 128
+            q = self.rng.integers(0, 256, (calib_batch, c, h, w))
+        else:
+            self.in_scale, self.in_zero = np.float32(1.0 / 127.0), 0
+            q = self.rng.integers(-127, 128, (calib_batch, c, h, w))
+        act = torch.from_numpy(((q - self.in_zero) * float(self.in_scale)).astype(np.float32))
+        self.input = _H(self.g.input(batch, c, h, w, self.in_scale, self.in_zero), act)
+
+    # ---- quantisation helpers ----
+    def _act_q(self, a):
+        a = a.detach().numpy()
+        if self.u8:
+            lo, hi = min(float(a.min()), 0.0), max(float(a.max()), 0.0)
+            scale = np.float32(max(hi - lo, 1e-6) / 255.0)
+            zp = int(np.clip(np.round(-lo / scale), 0, 255))
+            return scale, zp
+        return np.float32(max(float(np.abs(a).max()), 1e-6) / 127.0), 0
+
+    def _weight_q(self, w):
+        oc = w.shape[0]
+        if self.u8:
+            lo, hi = min(float(w.min()), 0.0), max(float(w.max()), 0.0)
+            scale = np.float32(max(hi - lo, 1e-8) / 255.0)
+            zp = int(np.clip(np.round(-lo / scale), 0, 255))
+            q = np.clip(np.round(w / scale + zp), 0, 255).astype(np.uint8)
+            return q, np.array([scale], np.float32), zp
+        s = (np.abs(w.reshape(oc, -1)).max(axis=1) / 127.0).astype(np.float32)
+        s = np.maximum(s, np.float32(1e-8))
+        q = np.clip(np.round(w / s.reshape((-1,) + (1,) * (w.ndim - 1))), -127, 127).astype(np.int8)
+        return q, s, 0
+
+    def _bias_q(self, b, s_in, ws):
+        return np.round(b / (np.float32(s_in) * ws.astype(np.float32))).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
+
+    def _fp_weight(self, oc, cg, kh, kw):
+        fan_in = cg * kh * kw
+        return (self.rng.standard_normal((oc, cg, kh, kw)) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+
+    # ---- ops ----
+    def conv(self, x, oc, k, stride=1, pad=0, group=1, activation=-1, bias=True, recipe=abi.RECIPE_HCL, dilation=1):
+        F = self.torch.nn.functional
+        c = self.g.dims(x.tid)[1]
+        w = self._fp_weight(oc, c // group, k, k)
+        b = (self.rng.standard_normal(oc) * 0.05).astype(np.float32) if bias else None
+        wq, ws, wz = self._weight_q(w)
+        s_in = self.g.tensors[x.tid]["scale"]
+        wdq = (wq.astype(np.float32) - wz) * ws.reshape((-1, 1, 1, 1) if not self.u8 else (1, 1, 1, 1))
+        bq = self._bias_q(b, s_in, ws if not self.u8 else ws[0] * np.ones(oc, np.float32)) if bias else None
+        bdq = None if bq is None else (bq.astype(np.float32) * np.float32(s_in) * (ws if not self.u8 else ws[0]))
+        a = F.conv2d(x.act, self.torch.from_numpy(wdq), None if bdq is None else self.torch.from_numpy(bdq.astype(np.float32)),
+                     stride=stride, padding=pad, dilation=dilation, groups=group)
+        if activation == 0:
+            a = F.relu(a)
+        elif activation == 6:
+            a = a.clamp(0, 6)
+        so, zo = self._act_q(a)
+        tid = self.g.conv(x.tid, wq, bq, ws, so, zo, stride=stride, pad=pad, dilation=dilation, group=group,
+                          activation=activation, recipe=recipe, weight_zero=wz)
+        return _H(tid, a)
+
+    def fc(self, x, oc, bias=True):
+        n, c, h, w = self.g.dims(x.tid)
+        k = c * h * w
+        wf = (self.rng.standard_normal((oc, k)) * np.sqrt(1.0 / k)).astype(np.float32)
+        b = (self.rng.standard_normal(oc) * 0.05).astype(np.float32) if bias else None
+        wq, ws, wz = self._weight_q(wf)
+        s_in = self.g.tensors[x.tid]["scale"]
+        wdq = (wq.astype(np.float32) - wz) * (ws.reshape(-1, 1) if not self.u8 else ws[0])
+        bq = self._bias_q(b, s_in, ws if not self.u8 else ws[0] * np.ones(oc, np.float32)) if bias else None
+        a = x.act.reshape(x.act.shape[0], -1) @ self.torch.from_numpy(wdq).T
+        if bq is not None:
+            a = a + self.torch.from_numpy((bq.astype(np.float32) * np.float32(s_in) * (ws if not self.u8 else ws[0])).astype(np.float32))
+        a = a.reshape(a.shape[0], oc, 1, 1)
+        so, zo = self._act_q(a)
+        return _H(self.g.fc(x.tid, wq, bq, ws, so, zo, weight_zero=wz), a)
+
+    def pool(self, x, method, kernel, stride, pad=0, global_pool=False):
+        F = self.torch.nn.functional
+        if global_pool:
+            a = x.act.mean(dim=(2, 3), keepdim=True) if method == abi.POOL_AVG else x.act.amax(dim=(2, 3), keepdim=True)
+        else:
+            p = (pad, pad, pad, pad) if np.isscalar(pad) else pad
+            # reference asymmetric pad: extra rows/cols at the bottom/right, never counted (caffe_flavor 0)
+            n, c, h, w = x.act.shape
+            oh = 1 + (h - kernel + 2 * p[0]) // stride
+            ow = 1 + (w - kernel + 2 * p[2]) // stride
+            ph1 = max((oh - 1) * stride + kernel - h - p[0], 0)
+            pw1 = max((ow - 1) * stride + kernel - w - p[2], 0)
+            if method == abi.POOL_MAX:
+                xp = F.pad(x.act, (p[2], pw1, p[0], ph1), value=float("-inf"))
+                a = F.max_pool2d(xp, kernel, stride)
+            else:
+                xp = F.pad(x.act, (p[2], pw1, p[0], ph1), value=0.0)
+                ones = F.pad(self.torch.ones_like(x.act), (p[2], pw1, p[0], ph1), value=0.0)
+                a = F.avg_pool2d(xp, kernel, stride) / F.avg_pool2d(ones, kernel, stride).clamp_min(1e-9)
+        so, zo = self._act_q(a)
+        tid = self.g.pool(x.tid, method, kernel, stride, pad, out_scale=so, out_zero=zo, global_pool=global_pool)
+        return _H(tid, a)
+
+    def relu(self, x, negative_slope=0.0):
+        a = self.torch.nn.functional.leaky_relu(x.act, negative_slope) if negative_slope else self.torch.relu(x.act)
+        so, zo = self._act_q(a)
+        return _H(self.g.relu(x.tid, so, zo, negative_slope), a)
+
+    def add(self, x, y):
+        a = x.act + y.act
+        so, zo = self._act_q(a)
+        return _H(self.g.eltwise(x.tid, y.tid, so, zo, abi.ELT_SUM), a)
+
+    def concat(self, xs):
+        a = self.torch.cat([x.act for x in xs], dim=1)
+        so, zo = self._act_q(a)
+        return _H(self.g.concat([x.tid for x in xs], so, zo), a)
+
+    def upsample(self, x, scale):
+        a = self.torch.nn.functional.interpolate(x.act, scale_factor=scale, mode="nearest")
+        return _H(self.g.upsample(x.tid, scale), a)
+
+    def identity(self, x):
+        return _H(self.g.identity(x.tid), x.act)
+
+    def finish(self, outs):
+        for o in outs:
+            self.g.mark_output(o.tid)
+        return self.g
+
+    def random_input(self, seed=42):
+        rng = np.random.default_rng(seed)
+        n, c, h, w = self.g.dims(self.input.tid)
+        if self.u8:
+            return rng.integers(0, 256, (n, c, h, w)).astype(np.uint8)
+        return rng.integers(-127, 128, (n, c, h, w)).astype(np.int8)
+
+
+def random_input(g, seed=42):
+    rng = np.random.default_rng(seed)
+    shape = g.dims(g.inputs[0])
+    if g.data_type == abi.DT_UINT8:
+        return rng.integers(0, 256, shape).astype(np.uint8)
+    return rng.integers(-127, 128, shape).astype(np.int8)
+
+
+def mobilenet_v1(data_type=abi.DT_INT8, batch=1, res=224, seed=1234, width=1.0, classes=1000, dw_recipe=None):
+    """MobileNet-v1 224 as in benchmark/models/mobilenet_benchmark.tmfile: 3x3 s2 stem, 13 x (dw3x3 + pw1x1), global
+    average pool, 1x1 classifier conv [1000,1024,1,1].  All convs carry a fused ReLU (activation = 0).
+    dw_recipe: recipe of the depthwise layers; the reference uses its HCL kernel at batch 1 and conv_ref
+    (conv_dw_hcl_x86.c:536 -> conv_ref.c) at batch > 1 for int8, conv_ref always for uint8."""
+    b = QuantBuilder(data_type, batch, 3, res, res, seed)
+    if dw_recipe is None:
+        dw_recipe = abi.RECIPE_REF if (batch > 1 or data_type == abi.DT_UINT8) else abi.RECIPE_HCL
+    ch = lambda c: max(8, int(c * width))
+    x = b.conv(b.input, ch(32), 3, stride=2, pad=1, activation=0)
+    cfg = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1),
+           (1024, 2), (1024, 1)]
+    for oc, s in cfg:
+        c = b.g.dims(x.tid)[1]
+        x = b.conv(x, c, 3, stride=s, pad=1, group=c, activation=0, recipe=dw_recipe)
+        x = b.conv(x, ch(oc), 1, activation=0)
+    x = b.pool(x, abi.POOL_AVG, 7, 1, global_pool=True)
+    x = b.conv(x, classes, 1, activation=-1)
+    return b.finish([x]), b
+
+
+def tiny_net(data_type=abi.DT_INT8, batch=2, seed=7):
+    """A few layers of every kind for fast CPU-oracle parity tests."""
+    b = QuantBuilder(data_type, batch, 3, 20, 20, seed)
+    x = b.conv(b.input, 16, 3, stride=2, pad=1, activation=0)
+    x = b.conv(x, 16, 3, stride=1, pad=1, group=16, activation=0, recipe=abi.RECIPE_REF)
+    x = b.conv(x, 32, 1, activation=0)
+    y = b.conv(x, 32, 3, pad=1, activation=6)
+    z = b.add(x, y)
+    z = b.relu(z)
+    p = b.pool(z, abi.POOL_MAX, 2, 2)
+    q = b.conv(p, 24, 1, activation=-1)
+    u = b.upsample(q, 2)
+    cat = b.concat([u, z])
+    l = b.relu(b.conv(cat, 40, 3, pad=1, activation=-1), negative_slope=0.1)
+    g = b.pool(l, abi.POOL_AVG, 10, 1, global_pool=True)
+    f = b.fc(g, 10)
+    return b.finish([f, l]), b
