@@ -188,3 +188,37 @@ class GraphDef:
             if L["bias"] is not None:
                 byts += 4 * oc
         return ops, byts
+
+    # ---- (de)serialisation for committed golden fixtures --------------------------------------------
+    _SCALARS = ("op", "output", "kernel_h", "kernel_w", "stride_h", "stride_w", "pad_h0", "pad_h1", "pad_w0", "pad_w1",
+                "dilation_h", "dilation_w", "group", "activation", "recipe", "pool_method", "pool_global", "caffe_flavor",
+                "negative_slope", "elt_type", "axis", "up_scale", "weight_zero", "bias_scale")
+
+    def to_dict(self):
+        import json
+
+        d = {"meta": np.frombuffer(json.dumps({
+            "data_type": self.data_type, "tensors": self.tensors, "inputs": self.inputs, "outputs": self.outputs,
+            "layers": [{**{k: L[k] for k in self._SCALARS}, "inputs": L["inputs"]} for L in self.layers]}).encode(),
+            dtype=np.uint8)}
+        for i, L in enumerate(self.layers):
+            for f in ("weight", "bias", "weight_scales"):
+                if L[f] is not None:
+                    d[f"L{i}_{f}"] = L[f]
+        return d
+
+    @classmethod
+    def from_dict(cls, d):
+        import json
+
+        meta = json.loads(bytes(d["meta"]).decode())
+        g = cls(meta["data_type"])
+        g.tensors = [dict(dims=tuple(t["dims"]), scale=t["scale"], zero_point=t["zero_point"]) for t in meta["tensors"]]
+        g.inputs, g.outputs = list(meta["inputs"]), list(meta["outputs"])
+        for i, L in enumerate(meta["layers"]):
+            L = dict(L)
+            for f in ("weight", "bias", "weight_scales"):
+                k = f"L{i}_{f}"
+                L[f] = np.ascontiguousarray(d[k]) if k in d else None
+            g.layers.append(L)
+        return g

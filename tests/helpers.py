@@ -1,0 +1,75 @@
+import json
+import os
+
+import numpy as np
+
+from tengine_b200 import abi
+from tengine_b200.graphdef import GraphDef
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    d = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g = GraphDef.from_dict(d)
+    ref = {int(k[5:]): v for k, v in d.items() if k.startswith("ref_t")}
+    return g, d["input"], ref
+
+
+def quant_u8(x, scale, zp):
+    # tests/op/test_timvx_op_convolution.cpp:120-132 get_uint8_data
+    return np.clip(np.round(np.asarray(x, np.float64) / scale + zp), 0, 255).astype(np.uint8)
+
+
+def kat_graphs():
+    """Build (name, GraphDef, input, expected_real, tolerance) from tests/golden/reference_kats.json."""
+    kats = json.load(open(os.path.join(GOLDEN, "reference_kats.json")))["kats"]
+    out = []
+    for k in kats:
+        u8 = k["dtype"] == "uint8"
+        g = GraphDef(abi.DT_UINT8 if u8 else abi.DT_INT8)
+        n, c, h, w = k["input_dims"]
+        x = g.input(n, c, h, w, k["input_scale"], k.get("input_zero", 0))
+        if "input_q" in k:
+            xin = np.array(k["input_q"], np.int8).reshape(n, c, h, w)
+        elif "input_fill" in k:
+            xin = quant_u8(np.full((n, c, h, w), k["input_fill"]), k["input_scale"], k["input_zero"])
+        else:
+            xin = quant_u8(k["input"], k["input_scale"], k["input_zero"]).reshape(n, c, h, w)
+        if k["op"] in ("conv", "fc"):
+            if u8:
+                wq = quant_u8(k["weight"], k["weight_scale"], k["weight_zero"]).reshape(k["weight_dims"])
+                ws, wz = [k["weight_scale"]], k["weight_zero"]
+            else:
+                wq = np.array(k["weight_q"], np.int8).reshape(k["weight_dims"])
+                ws, wz = k["weight_scales"], 0
+            bq = np.array(k["bias_q"], np.int32) if "bias_q" in k else None
+            if k["op"] == "conv":
+                y = g.conv(x, wq, bq, ws, k["output_scale"], k.get("output_zero", 0), stride=k["stride"], pad=k["pad"],
+                           group=k["group"], activation=k["activation"], weight_zero=wz)
+            else:
+                y = g.fc(x, wq, bq, ws, k["output_scale"], k.get("output_zero", 0), weight_zero=wz)
+        else:
+            y = g.pool(x, abi.POOL_MAX if k["method"] == "max" else abi.POOL_AVG, k["kernel"], k["stride"], k["pad"],
+                       out_scale=k["output_scale"], out_zero=k.get("output_zero", 0))
+        g.mark_output(y)
+        if "expected_fill" in k:
+            exp = np.full(g.dims(y), k["expected_fill"], np.float64)
+        else:
+            exp = np.array(k["expected"], np.float64).reshape(g.dims(y))
+        out.append((k["name"], g, xin, exp, k.get("tolerance", 0.1)))
+    return out
+
+
+def dequant(g, t, q):
+    ti = g.tensors[t]
+    return (q.astype(np.float64) - ti["zero_point"]) * ti["scale"]
+
+
+def layer_outputs(g):
+    return [L["output"] for L in g.layers]
+
+
+def diff_stats(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return int(d.max()), int((d > 0).sum())
