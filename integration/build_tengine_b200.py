@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Integration build: the reference Tengine library WITH the B200 device compiled in, exactly as its CMake would do for
+"""Integration build (test/demo infrastructure, not part of the product package): the reference Tengine library WITH the B200 device compiled in, exactly as its CMake would do for
 `source/device/b200/` + one `_REGISTER_DEVICE_LIST` entry (source/device/CMakeLists.txt:63-188), but driven by gcc directly.
 
   build/tengine/libtengine-lite.so            reference objects (oracle/_ref/obj, untouched sources) + b200_device.cc
@@ -15,8 +15,8 @@ import shutil
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tengine_b200", "device")  # the device sources (would be source/device/b200/ in-tree)
 sys.path.insert(0, ROOT)
 from oracle import build_ref as br  # noqa: E402
 

@@ -95,3 +95,13 @@ class Reference:
         if rc != 0:
             raise RuntimeError(f"reference run failed rc={rc}")
         return dict(zip(want, outs)), (stats[0], stats[1])
+
+
+def save_tmfile(ref, g, path):
+    """Write GraphDef `g` as a Tengine tmfile with the reference's own writer (tools/save_graph/save_graph.cpp)."""
+    T, L = g.c_tables()
+    ref.lib.ref_shim_save_tmfile.restype = C.c_int
+    rc = ref.lib.ref_shim_save_tmfile(T, len(g.tensors), L, len(g.layers), g.id_array(g.inputs), len(g.inputs),
+                                      g.id_array(g.outputs), len(g.outputs), path.encode())
+    if rc != 0:
+        raise RuntimeError(f"save_tmfile failed rc={rc}")

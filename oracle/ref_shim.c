@@ -55,14 +55,35 @@ static tensor_t make_const(graph_t graph, const char* name, int dtype, const int
     return t;
 }
 
-/* Returns 0 on success.  `want_ids` tensors (must be layer outputs) are marked graph outputs and copied to
- * out_bufs after the last run.  ms_stats[0]=min, [1]=avg over `loops` timed run_graph calls (after `warmup`). */
-SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
-                          int num_layers, const int* input_ids, int num_inputs, const int* want_ids, int num_want,
-                          const void* const* in_bufs, void* const* out_bufs, const char* device_name,
-                          int num_thread, int warmup, int loops, double* ms_stats)
+struct built
+{
+    graph_t graph;
+    context_t ctx;
+    tensor_t* tt;
+    char** out_node_name;
+    int precision;
+};
+
+static void free_built(struct built* b, int num_tensors)
+{
+    if (b->graph) destroy_graph(b->graph);
+    if (b->ctx) destroy_context(b->ctx);
+    if (b->out_node_name)
+        for (int i = 0; i < num_tensors; i++) free(b->out_node_name[i]);
+    free(b->out_node_name);
+    free(b->tt);
+    memset(b, 0, sizeof *b);
+}
+
+/* Build the Tengine graph for (tensors, layers).  `want_ids` tensors are marked graph outputs; when out_bufs is given
+ * they also receive the caller's buffers before prerun. */
+static int build_graph(struct built* B, const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
+                       int num_layers, const int* input_ids, int num_inputs, const int* want_ids, int num_want,
+                       void* const* out_bufs, const char* device_name)
 {
     int rc = -1;
+    memset(B, 0, sizeof *B);
+
     if (!g_inited)
     {
         if (init_tengine() != 0) return -100;
@@ -93,7 +114,7 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
         snprintf(name, sizeof name, "in%d", input_ids[i]);
         node_t node = create_graph_node(graph, name, "InputOp");
         tensor_t t = create_graph_tensor(graph, name, d->data_type);
-        if (!node || !t) goto done;
+        if (!node || !t) goto fail;
         set_node_output_tensor(node, 0, t, TENSOR_TYPE_INPUT);
         set_tensor_shape(t, d->dims, 4);
         set_tensor_quant_param(t, &d->scale, &d->zero_point, 1);
@@ -118,16 +139,11 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
         case TB200_OP_CONCAT: opname = "Concat"; break;
         case TB200_OP_UPSAMPLE: opname = "Upsample"; break;
         case TB200_OP_IDENTITY: opname = "Dropout"; break;
-        default: goto done;
+        default: goto fail;
         }
-        snprintf(name, sizeof name, "L%d", li);
-        struct node* node = (struct node*)create_graph_node(graph, name, opname);
-        if (!node) goto done;
-        for (int k = 0; k < L->num_inputs; k++)
-        {
-            if (!tt[L->inputs[k]]) { fprintf(stderr, "ref_shim: layer %d input %d undefined\n", li, k); goto done; }
-            set_node_input_tensor(node, k, tt[L->inputs[k]]);
-        }
+        /* Const nodes are created BEFORE the node that consumes them: the tmfile writer and the graph splitter assume
+         * node indices are in topological order (tools/save_graph/save_graph.cpp:233-244, optimizer/split.c:146-160). */
+        tensor_t wt = NULL, bt = NULL;
         if (L->op == TB200_OP_CONV || L->op == TB200_OP_FC)
         {
             const int is_u8 = din->data_type == TENGINE_DT_UINT8;
@@ -149,7 +165,6 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
             int* zps = (int*)calloc(oc, sizeof(int));
             float* bscales = (float*)calloc(oc, sizeof(float));
             snprintf(name, sizeof name, "L%d_w", li);
-            tensor_t wt;
             if (is_u8)
             {
                 int wz = L->weight_zero;
@@ -161,30 +176,37 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
                 wt = make_const(graph, name, TENGINE_DT_INT8, wdims, wn, L->weight, wbytes, L->weight_scales, zps, oc);
                 for (int c = 0; c < oc; c++) bscales[c] = din->scale * L->weight_scales[c];
             }
-            if (!wt) goto done;
-            set_node_input_tensor(node, 1, wt);
+            if (!wt) goto fail;
             if (L->bias)
             {
                 snprintf(name, sizeof name, "L%d_b", li);
                 int bd[1] = {oc};
-                tensor_t bt = make_const(graph, name, TENGINE_DT_INT32, bd, 1, L->bias, oc * 4, bscales, zps, is_u8 ? 1 : oc);
-                if (!bt) goto done;
-                set_node_input_tensor(node, 2, bt);
+                bt = make_const(graph, name, TENGINE_DT_INT32, bd, 1, L->bias, oc * 4, bscales, zps, is_u8 ? 1 : oc);
+                if (!bt) goto fail;
             }
             free(zps);
             free(bscales);
         }
         snprintf(name, sizeof name, "L%d", li);
+        struct node* node = (struct node*)create_graph_node(graph, name, opname);
+        if (!node) goto fail;
+        for (int k = 0; k < L->num_inputs; k++)
+        {
+            if (!tt[L->inputs[k]]) { fprintf(stderr, "ref_shim: layer %d input %d undefined\n", li, k); goto fail; }
+            set_node_input_tensor(node, k, tt[L->inputs[k]]);
+        }
+        if (wt) set_node_input_tensor(node, 1, wt);
+        if (bt) set_node_input_tensor(node, 2, bt);
         tensor_t ot = create_graph_tensor(graph, name, dout->data_type);
         set_node_output_tensor(node, 0, ot, TENSOR_TYPE_VAR);
         set_tensor_quant_param(ot, &dout->scale, &dout->zero_point, 1);
         /* Requested tensors get the caller's buffer BEFORE prerun: the CPU device's memory pool only manages
          * tensors whose data is still NULL (cpu_pool.c:290-291), so they are never recycled or run in place. */
         for (int k = 0; k < num_want; k++)
-            if (want_ids[k] == L->output)
+            if (out_bufs && want_ids[k] == L->output)
             {
                 set_tensor_shape(ot, dout->dims, 4);
-                if (set_tensor_buffer(ot, out_bufs[k], dout->dims[0] * dout->dims[1] * dout->dims[2] * dout->dims[3]) < 0) goto done;
+                if (set_tensor_buffer(ot, out_bufs[k], dout->dims[0] * dout->dims[1] * dout->dims[2] * dout->dims[3]) < 0) goto fail;
             }
         tt[L->output] = ot;
         out_node_name[L->output] = strdup(name);
@@ -228,16 +250,38 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
     {
         const char** names = (const char**)calloc(num_inputs + num_want, sizeof(char*));
         for (int i = 0; i < num_inputs; i++) names[i] = out_node_name[input_ids[i]];
-        if (set_graph_input_node(graph, names, num_inputs) < 0) goto done;
+        if (set_graph_input_node(graph, names, num_inputs) < 0) goto fail;
         for (int i = 0; i < num_want; i++)
         {
-            if (!out_node_name[want_ids[i]]) goto done;
+            if (!out_node_name[want_ids[i]]) goto fail;
             names[i] = out_node_name[want_ids[i]];
         }
-        if (set_graph_output_node(graph, names, num_want) < 0) goto done;
+        if (set_graph_output_node(graph, names, num_want) < 0) goto fail;
         free(names);
     }
 
+    B->graph = graph, B->ctx = ctx, B->tt = tt, B->out_node_name = out_node_name, B->precision = precision;
+    return 0;
+fail:
+    B->graph = graph, B->ctx = ctx, B->tt = tt, B->out_node_name = out_node_name;
+    free_built(B, num_tensors);
+    return rc;
+}
+
+/* Returns 0 on success.  `want_ids` tensors (layer outputs) are marked graph outputs and returned in out_bufs.
+ * ms_stats[0]=min, [1]=avg over `loops` timed run_graph calls (after `warmup`). */
+SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
+                          int num_layers, const int* input_ids, int num_inputs, const int* want_ids, int num_want,
+                          const void* const* in_bufs, void* const* out_bufs, const char* device_name,
+                          int num_thread, int warmup, int loops, double* ms_stats)
+{
+    struct built B;
+    int rc = build_graph(&B, tensors, num_tensors, layers, num_layers, input_ids, num_inputs, want_ids, num_want, out_bufs, device_name);
+    if (rc != 0) return rc;
+    graph_t graph = B.graph;
+    tensor_t* tt = B.tt;
+    int precision = B.precision;
+    rc = -1;
     struct options opt;
     opt.num_thread = num_thread;
     opt.cluster = TENGINE_CLUSTER_ALL;
@@ -298,11 +342,24 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
 done_postrun:
     postrun_graph(graph);
 done:
-    destroy_graph(graph);
-    if (ctx) destroy_context(ctx);
-    for (int i = 0; i < num_tensors; i++) free(out_node_name[i]);
-    free(out_node_name);
-    free(tt);
+    free_built(&B, num_tensors);
+    return rc;
+}
+
+/* Write the graph as a tmfile with the reference's own writer (tools/save_graph/save_graph.cpp:400): the int8/uint8
+ * models the UNMODIFIED tm_classification_int8/uint8 and tm_benchmark binaries are then run on. */
+extern int ref_shim_save_graph_cxx(void* graph, const char* fname);
+extern int infer_ir_graph_shape(struct graph* graph);
+SHIM_API int ref_shim_save_tmfile(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
+                                  int num_layers, const int* input_ids, int num_inputs, const int* output_ids,
+                                  int num_outputs, const char* fname)
+{
+    struct built B;
+    int rc = build_graph(&B, tensors, num_tensors, layers, num_layers, input_ids, num_inputs, output_ids, num_outputs, NULL, NULL);
+    if (rc != 0) return rc;
+    if (infer_ir_graph_shape((struct graph*)B.graph) != 0) rc = -110;
+    else rc = ref_shim_save_graph_cxx(B.graph, fname);
+    free_built(&B, num_tensors);
     return rc;
 }
 

@@ -30,6 +30,13 @@ struct EpiParams
     int32_t is_uint8;
     int32_t fc_rounding;
     int32_t has_bias;
+    // ---- fast path (see requant_fast) ----
+    const float* fast_m; // [OCp] int8: M[oc] ~ s_in*s_w[oc]/s_out (FC: exactly the reference's requant scale);
+                         //       uint8: the bias term in real units, exactly as the reference rounds it
+    float fast_lo, fast_hi;   // clamp of t = f/s_out: activation and the +-127 / 0..255 saturation folded together
+    float fast_flo, fast_fhi; // uint8: activation clamp in real units
+    float fast_r;             // uint8: fl(1/s_out)
+    int32_t fast_ok;          // 0: scales are degenerate, always take the exact path
 };
 
 // C round(): half away from zero, exact for every float (CUDA's roundf is the exact, slow-path version).
@@ -116,6 +123,51 @@ __device__ __forceinline__ int requant(int32_t acc, int oc, const EpiParams& e)
         q = q < 0 ? 0 : q;
         return q;
     }
+}
+
+// Fast requantisation with an exactness guarantee.
+//
+// The reference rounds t_ref = fl(fl(fl(x*s_in)*s_w)/s_out) (three roundings) half away from zero.  The fast path forms
+// t = fl(x*M) with M = fl(s_in*s_w/s_out computed in double): |t - t_ref| <= 5*2^-24*|t| < 4e-5 inside the clamp range
+// [-127,127].  Rounding t to nearest (magic-number add) therefore gives the reference's integer unless t lies within
+// kTieEps of a half-integer; exactly those elements (about 2.4e-4 of them) are recomputed with the literal reference
+// arithmetic (requant()).  Clamps commute with the monotone division/rounding, so activation and saturation are applied
+// to t directly.  For FC the reference itself computes roundf(x*rq) and M = rq exactly, so t == t_ref.
+// Cost: ~10 instructions per element instead of ~60 (IEEE division + roundf).
+#define TB200_MAGIC 12582912.0f // 1.5 * 2^23
+#define TB200_TIE_EPS 1.220703125e-4f // 2^-13
+
+__device__ __forceinline__ int requant_fast(int32_t acc, int oc, const EpiParams& e, float m, int32_t b)
+{
+    if (!e.is_uint8)
+    {
+        float t = __fmul_rn((float)(acc + b), m);
+        t = fmaxf(t, e.fast_lo);
+        t = fminf(t, e.fast_hi);
+        const float r = __fadd_rn(t, TB200_MAGIC);
+        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
+        if (fabsf(d) > 0.5f - TB200_TIE_EPS) return requant(acc, oc, e);
+        return __float_as_int(r) & 0xff;
+    }
+    else
+    {
+        // f is bit-identical to the reference's (same operations); only the division is replaced by *fl(1/s_out)
+        float f = __fadd_rn(__fmul_rn((float)acc, e.in_w_scale), m);
+        f = fminf(fmaxf(f, e.fast_flo), e.fast_fhi);
+        float t = __fmul_rn(f, e.fast_r);
+        t = fminf(fmaxf(t, e.fast_lo), e.fast_hi);
+        const float r = __fadd_rn(t, TB200_MAGIC);
+        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
+        if (fabsf(d) > 0.5f - TB200_TIE_EPS) return requant(acc, oc, e);
+        return (__float_as_int(r) - 0x4B400000 + e.out_zero) & 0xff;
+    }
+}
+
+// per-channel operands of the fast path: (m, bias)
+__device__ __forceinline__ int requant_auto(int32_t acc, int oc, const EpiParams& e)
+{
+    if (!e.fast_ok) return requant(acc, oc, e);
+    return requant_fast(acc, oc, e, __ldg(e.fast_m + oc), (e.has_bias && !e.is_uint8) ? __ldg(e.bias + oc) : 0);
 }
 
 __device__ __forceinline__ int dp4a_s8(int a, int b, int c) { return __dp4a(a, b, c); }

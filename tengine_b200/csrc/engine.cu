@@ -6,6 +6,7 @@
 // analogue of cpu_device.c:97-221 with every node executing on the GPU.  No CPU compute path exists here.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -203,12 +204,41 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
     e.fc_rounding = fc ? 1 : 0;
     e.has_bias = L.bias != nullptr;
     e.in_w_scale = e.is_uint8 ? tin.scale * L.weight_scales[0] : 0.f; // fp32 product, as bias_scale in conv_kernel_x86.c:1723
+    // fast-path constants (common.cuh requant_fast): clamps of t = f / s_out with activation and saturation folded in
+    const float so = tout.scale;
+    const float inf = __builtin_inff();
+    const int act = fc ? -1 : L.activation;
+    float flo = -inf, fhi = inf; // activation clamp in real units
+    if (L.recipe == TB200_RECIPE_HCL || fc)
+    {
+        if (act == 0) flo = 0.f;
+        if (act > 0) flo = 0.f, fhi = 6.f;
+    }
+    else if (act >= 0)
+    {
+        if (act == 1) flo = -1.f, fhi = 1.f;
+        else flo = 0.f, fhi = (act == 6) ? 6.f : inf;
+    }
+    e.fast_flo = flo, e.fast_fhi = fhi;
+    if (e.is_uint8)
+    {
+        e.fast_lo = (float)(0 - tout.zero_point), e.fast_hi = (float)(255 - tout.zero_point);
+        e.fast_r = 1.0f / so;
+    }
+    else
+    {
+        e.fast_lo = -127.f, e.fast_hi = 127.f;
+        if (flo > -inf) e.fast_lo = fmaxf(-127.f, flo / so); // fl(x / s_out): the same rounded quotient the reference forms
+        if (fhi < inf) e.fast_hi = fminf(127.f, fhi / so);
+        e.fast_r = 0.f;
+    }
+    e.fast_ok = (so > 1e-30f && so < 1e30f && tin.scale > 1e-30f && tin.scale < 1e30f) ? 1 : 0;
     return e;
 }
 
 struct WeightBlob
 {
-    size_t w_off, bias_off, scale_off, w_size;
+    size_t w_off, bias_off, scale_off, fast_off, w_size;
 };
 
 static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
@@ -372,6 +402,8 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             wtotal += align_up((size_t)tout.cp * 4, 256);
             blobs[li].scale_off = wtotal;
             wtotal += align_up((size_t)tout.cp * 4, 256);
+            blobs[li].fast_off = wtotal;
+            wtotal += align_up((size_t)tout.cp * 4, 256);
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
@@ -440,10 +472,22 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             }
             int32_t* b = (int32_t*)(img.data() + blobs[li].bias_off);
             float* sc = (float*)(img.data() + blobs[li].scale_off);
+            float* fm = (float*)(img.data() + blobs[li].fast_off);
+            const bool fc = L.op == TB200_OP_FC;
             for (int o = 0; o < tout.cp; o++)
             {
                 b[o] = (L.bias && o < OC) ? L.bias[o] : 0;
                 sc[o] = u8 ? L.weight_scales[0] : (o < OC ? L.weight_scales[o] : 1.f);
+                if (u8)
+                {
+                    // the bias term in real units, rounded exactly as the reference rounds it
+                    const float S = tin.d.scale * L.weight_scales[0];
+                    fm[o] = (L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0];
+                }
+                else if (fc)
+                    fm[o] = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
+                else
+                    fm[o] = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
             }
         }
         CUDA_OK(cudaMemcpyAsync(g->w_arena, img.data(), g->w_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -478,6 +522,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.epi = make_epi(L, tin.d, tout.d, fc);
             s.epi.bias = (const int32_t*)(g->w_arena + blobs[li].bias_off);
             s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
+            s.epi.fast_m = (const float*)(g->w_arena + blobs[li].fast_off);
             ConvShape& cs = s.cs;
             cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
             if (fc)
@@ -727,6 +772,7 @@ static EpiParams epi_from_abi(const tb200k_epilogue* e)
     p.in_zero = e->in_zero, p.w_zero = e->w_zero, p.out_zero = e->out_zero, p.activation = e->activation, p.recipe = e->recipe;
     p.is_uint8 = e->is_uint8, p.fc_rounding = e->fc_rounding, p.has_bias = e->bias != nullptr;
     p.in_w_scale = e->in_scale * e->w_scale_tensor;
+    p.fast_ok = 0; // the raw kernel entry points always use the literal reference arithmetic
     return p;
 }
 static ConvShape shape_from_abi(const tb200k_conv_shape* s)

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restr
                 int a = acc[j + t];
                 if (U8) // sum (x-zx)(w-zw) = Sxw - zw*Sx - zx*Sw + cnt*zx*zw   (cnt counts REAL channels only)
                     a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.cg * e.in_zero * e.w_zero;
-                q = requant(a, oc, e);
+                q = requant_auto(a, oc, e);
             }
             packed |= (unsigned)q << (8 * t);
         }
@@ -145,10 +145,99 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict_
     for (int t = 0; t < 4; t++)
     {
         const int c = c4 * 4 + t;
-        const int q = (c < s.oc) ? requant(acc[t], c, e) : 0;
+        const int q = (c < s.oc) ? requant_auto(acc[t], c, e) : 0;
         packed |= (unsigned)q << (8 * t);
     }
     reinterpret_cast<unsigned*>(out + (size_t)pix * s.ocp)[c4] = packed;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Depthwise 3x3, int8, stride 1 or 2, dilation 1: the MobileNet hot depthwise path.
+// Thread = 4 channels (one 32-bit word) x TW consecutive output pixels of one output row; the 3 x ((TW-1)*S+3) input
+// window is loaded once and slides through registers, so each input word is fetched once per thread instead of up to
+// 9 times.  A MAC is ONE dp4a: the weight word is split into four one-hot-byte words (w & 0xff<<8j), so
+// dp4a(x_word, w_j, acc) = x[byte j] * w[byte j] + acc with no unpacking of the activations.
+// Takes the role of convdw3x3s1_int8_sse / convdw3x3s2_int8_sse (conv_dw_hcl_x86.c:97-445).
+// ------------------------------------------------------------------------------------------------------
+template <int TW, int S>
+__global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
+                                                            uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+{
+    const int cw = s.cp / 4;
+    const int gpr = (s.ow + TW - 1) / TW; // pixel groups per output row
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)s.n * s.oh * gpr * cw;
+    if (idx >= total) return;
+    const int c4 = (int)(idx % cw);
+    long long r = idx / cw;
+    const int pg = (int)(r % gpr);
+    r /= gpr;
+    const int oh = (int)(r % s.oh);
+    const int n = (int)(r / s.oh);
+    const int ow0 = pg * TW;
+
+    int wj[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+    {
+        const unsigned wv = __ldg(reinterpret_cast<const unsigned*>(wgt + (size_t)t * s.cp) + c4);
+#pragma unroll
+        for (int j = 0; j < 4; j++) wj[t][j] = (int)(wv & (0xffu << (8 * j)));
+    }
+    int acc[TW][4];
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[t][j] = 0;
+
+    constexpr int COLS = (TW - 1) * S + 3;
+    const int ix0 = ow0 * S - s.pw0;
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+    {
+        const int iy = oh * S - s.ph0 + kh;
+        if (iy < 0 || iy >= s.h) continue;
+        const unsigned* rowp = reinterpret_cast<const unsigned*>(in + ((size_t)n * s.h + iy) * s.w * s.cp) + c4;
+        int xv[COLS];
+#pragma unroll
+        for (int col = 0; col < COLS; col++)
+        {
+            const int ix = ix0 + col;
+            xv[col] = (ix >= 0 && ix < s.w) ? (int)__ldg(rowp + (size_t)ix * cw) : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[t][j] = dp4a_s8(xv[t * S + kw], wj[kh * 3 + kw][j], acc[t][j]);
+    }
+
+    float m[4];
+    int b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const int c = c4 * 4 + j;
+        m[j] = e.fast_ok ? __ldg(e.fast_m + c) : 0.f;
+        b[j] = e.has_bias ? __ldg(e.bias + c) : 0;
+    }
+    uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+    {
+        if (ow0 + t >= s.ow) break;
+        unsigned packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const int c = c4 * 4 + j;
+            int q = 0;
+            if (c < s.oc) q = e.fast_ok ? requant_fast(acc[t][j], c, e, m[j], b[j]) : requant(acc[t][j], c, e);
+            packed |= (unsigned)q << (8 * j);
+        }
+        reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = packed;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -217,7 +306,7 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const uint8_t* __restric
             {
                 int a = acc[j + t];
                 if (U8) a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.c * e.in_zero * e.w_zero;
-                q = requant(a, oc, e);
+                q = requant_auto(a, oc, e);
             }
             packed |= (unsigned)q << (8 * t);
         }
@@ -486,6 +575,23 @@ cudaError_t launch_conv_direct(const void* in, const void* w, void* out, const C
 
 cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
 {
+    if (!e.is_uint8 && s.kh == 3 && s.kw == 3 && s.dh == 1 && s.dw == 1 && s.sh == s.sw && (s.sh == 1 || s.sh == 2))
+    {
+        const int cw = s.cp / 4;
+        if (s.sh == 1)
+        {
+            constexpr int TW = 8;
+            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            conv_dw3x3_i8_kernel<TW, 1><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        }
+        else
+        {
+            constexpr int TW = 4;
+            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            conv_dw3x3_i8_kernel<TW, 2><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        }
+        return cudaGetLastError();
+    }
     const long long total = (long long)s.n * s.oh * s.ow * (s.cp / 4);
     if (e.is_uint8) conv_dw_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     else conv_dw_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
@@ -495,6 +601,13 @@ cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvS
 cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
 {
     const long long npix = (long long)s.n * s.oh * s.ow;
+    if (s.ocp % 32 == 0)
+    {
+        dim3 grid(blocks_for(npix, 128), s.ocp / 32);
+        if (e.is_uint8) conv_stem_kernel<true, 32><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        else conv_stem_kernel<false, 32><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        return cudaGetLastError();
+    }
     dim3 grid(blocks_for(npix, 128), s.ocp / 16);
     if (e.is_uint8) conv_stem_kernel<true, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     else conv_stem_kernel<false, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);

@@ -1,0 +1,96 @@
+"""The drop-in boundary, end to end: the REAL Tengine runtime (unmodified reference sources + the B200 nn_device of
+tengine_b200/device/, built by integration/build_tengine_b200.py into build/tengine/) executes graphs on device "B200"
+through init_tengine()/create_graph()/prerun_graph_multithread()/run_graph(), and the UNMODIFIED example binaries
+tm_classification_int8 / tm_benchmark run against it.  Results are compared with the same library's CPU device."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build", "tengine")
+MODELS = os.path.join(ROOT, "oracle", "_ref", "models")
+
+
+def _have_integration():
+    return os.path.exists(os.path.join(BUILD, "libtengine-lite.so")) and os.path.exists(os.path.join(BUILD, "libref_shim.so"))
+
+
+def test_integration_library_registers_b200_and_fails_loudly_without_gpu(tmp_path):
+    """CPU-only check: the device is registered in-tree, the splitter hands it the graph, and without a GPU pre_run fails
+    with an error (no silent CPU fallback)."""
+    if not _have_integration():
+        pytest.skip("integration build absent (needs /root/reference): python integration/build_tengine_b200.py")
+    from tengine_b200 import runtime as rt
+
+    if rt.device_count() > 0:
+        pytest.skip("a B200 is visible")
+    out = tmp_path / "o.npz"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "run_fixture.py"), "ref_tiny_int8", "B200", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device visible" in (r.stderr + r.stdout)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "run_fixture.py"), "ref_tiny_int8", "CPU", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_tiny_int8", "ref_mobilenet025_int8", "ref_tiny_uint8", "ref_mobilenet025_uint8"])
+def test_graph_on_b200_device_through_tengine_runtime(tmp_path, name):
+    if not _have_integration():
+        pytest.skip("integration build absent")
+    outs = {}
+    for dev in ("CPU", "B200"):
+        out = tmp_path / f"{dev}.npz"
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "run_fixture.py"), name, dev, str(out)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (dev, r.stderr[-1500:])
+        outs[dev] = dict(np.load(out))
+    for k in outs["CPU"]:
+        if k == "ms":
+            continue
+        d = np.abs(outs["CPU"][k].astype(int) - outs["B200"][k].astype(int))
+        if "int8" in name and "uint8" not in name:
+            assert d.max() == 0, (k, int(d.max()))
+        else:
+            assert d.max() <= 2, (k, int(d.max()))  # uint8: the CPU path is an fp32 simulation (+-1 LSB per layer)
+
+
+@pytest.mark.gpu
+def test_unmodified_tm_classification_int8_on_b200():
+    """examples/tm_classification_int8.c, compiled unmodified, passes no context (create_graph(NULL, ...)): the
+    TG_DEFAULT_DEVICE=B200 seam routes its graph to the device.  Same top-5 as the CPU device."""
+    exe = os.path.join(BUILD, "tm_classification_int8")
+    model = os.path.join(MODELS, "mobilenet_v1_int8.tmfile")
+    img = os.path.join(MODELS, "test.bmp")
+    if not (os.path.exists(exe) and os.path.exists(model) and os.path.exists(img)):
+        pytest.skip("integration build / model files absent")
+    res = {}
+    for dev in ("CPU", "B200"):
+        env = dict(os.environ)
+        env.pop("TG_DEFAULT_DEVICE", None)
+        if dev == "B200":
+            env["TG_DEFAULT_DEVICE"] = "B200"
+        r = subprocess.run([exe, "-m", model, "-i", img, "-g", "224,224", "-r", "2", "-t", "8"], capture_output=True, text=True,
+                           env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        txt = r.stdout + r.stderr
+        top = [l.strip() for l in txt.splitlines() if "," in l and l.strip()[0].isdigit() or l.strip().startswith("-")]
+        res[dev] = [l for l in txt.splitlines() if l.count(",") == 1 and l.strip().replace(".", "").replace(",", "").replace(" ", "").replace("-", "").isdigit()]
+        assert len(res[dev]) == 5, txt[-800:]
+    assert res["CPU"] == res["B200"]
+
+
+@pytest.mark.gpu
+def test_unmodified_tm_benchmark_on_b200():
+    exe = os.path.join(BUILD, "tm_benchmark")
+    model = os.path.join(MODELS, "mobilenet_v1_int8.tmfile")
+    if not (os.path.exists(exe) and os.path.exists(model)):
+        pytest.skip("integration build / model files absent")
+    r = subprocess.run([exe, "-d", "B200", "-m", model, "-i", "8,3,224,224", "-f", "2", "-r", "5", "-t", "8"], capture_output=True,
+                       text=True, timeout=600)
+    txt = r.stdout + r.stderr
+    assert r.returncode == 0 and "min =" in txt, txt[-800:]
