@@ -55,9 +55,9 @@ def main(ref="/root/reference"):
         br.build_apps(ref, verbose=False)
     finally:
         br.OUT = save_out
-    subprocess.check_call([br.CC, "-O2", "-shared", "-fPIC", "-w", f"-I{ref}/source", f"-I{gen}/source",
-                           f"-I{ref}/source/operator/prototype", os.path.join(ROOT, "oracle", "ref_shim.c"), "-o",
-                           os.path.join(OUT, "libref_shim.so"), f"-L{OUT}", "-ltengine-lite", "-Wl,-rpath,$ORIGIN"])
+    from oracle import build_shim
+
+    build_shim.main(ref, OUT)
     print(f"[integration] {lib} (+ apps, shim) built")
 
 

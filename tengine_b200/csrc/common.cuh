@@ -31,8 +31,8 @@ struct EpiParams
     int32_t fc_rounding;
     int32_t has_bias;
     // ---- fast path (see requant_fast) ----
-    const float* fast_m; // [OCp] int8: M[oc] ~ s_in*s_w[oc]/s_out (FC: exactly the reference's requant scale);
-                         //       uint8: the bias term in real units, exactly as the reference rounds it
+    const float2* fast_par; // [OCp] int8: (M[oc] ~ s_in*s_w[oc]/s_out [FC: exactly the reference's requant scale], bias bits);
+                            //       uint8: (the bias term in real units, exactly as the reference rounds it, 0)
     float fast_lo, fast_hi;   // clamp of t = f/s_out: activation and the +-127 / 0..255 saturation folded together
     float fast_flo, fast_fhi; // uint8: activation clamp in real units
     float fast_r;             // uint8: fl(1/s_out)
@@ -67,7 +67,7 @@ __device__ __forceinline__ float act_ref(float t, int activation)
 
 // acc = exact integer dot product (int8: sum x*w; uint8: sum (x-zx)(w-zw) over in-bounds taps), WITHOUT bias.
 // Returns the output byte (int8 bit pattern or uint8).
-__device__ __forceinline__ int requant(int32_t acc, int oc, const EpiParams& e)
+static __device__ __noinline__ int requant(int32_t acc, int oc, const EpiParams& e)
 {
     const int32_t b = e.has_bias ? __ldg(e.bias + oc) : 0;
     if (!e.is_uint8)
@@ -137,37 +137,85 @@ __device__ __forceinline__ int requant(int32_t acc, int oc, const EpiParams& e)
 #define TB200_MAGIC 12582912.0f // 1.5 * 2^23
 #define TB200_TIE_EPS 1.220703125e-4f // 2^-13
 
-__device__ __forceinline__ int requant_fast(int32_t acc, int oc, const EpiParams& e, float m, int32_t b)
+// One element: returns the bit pattern of r = t + MAGIC (low byte = the rounded, clamped integer) and ORs `bit` into
+// `bad` when t is inside the tie guard band.  ~10 instructions; U8 is a compile-time switch so no per-element branch.
+template <bool U8>
+__device__ __forceinline__ uint32_t requant_fast_bits(int32_t acc, const EpiParams& e, float m, int32_t b, uint32_t& bad, uint32_t bit)
 {
-    if (!e.is_uint8)
-    {
-        float t = __fmul_rn((float)(acc + b), m);
-        t = fmaxf(t, e.fast_lo);
-        t = fminf(t, e.fast_hi);
-        const float r = __fadd_rn(t, TB200_MAGIC);
-        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
-        if (fabsf(d) > 0.5f - TB200_TIE_EPS) return requant(acc, oc, e);
-        return __float_as_int(r) & 0xff;
-    }
+    float t;
+    if (!U8)
+        t = __fmul_rn((float)(acc + b), m);
     else
     {
-        // f is bit-identical to the reference's (same operations); only the division is replaced by *fl(1/s_out)
+        // f is bit-identical to the reference's (same operations); only the division is replaced by * fl(1/s_out)
         float f = __fadd_rn(__fmul_rn((float)acc, e.in_w_scale), m);
         f = fminf(fmaxf(f, e.fast_flo), e.fast_fhi);
-        float t = __fmul_rn(f, e.fast_r);
-        t = fminf(fmaxf(t, e.fast_lo), e.fast_hi);
-        const float r = __fadd_rn(t, TB200_MAGIC);
-        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
-        if (fabsf(d) > 0.5f - TB200_TIE_EPS) return requant(acc, oc, e);
-        return (__float_as_int(r) - 0x4B400000 + e.out_zero) & 0xff;
+        t = __fmul_rn(f, e.fast_r);
     }
+    t = fminf(fmaxf(t, e.fast_lo), e.fast_hi);
+    const float r = __fadd_rn(t, TB200_MAGIC);
+    const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
+    // bad |= bit when |d| > 0.5 - eps : one FSETP (|d| folds into the operand modifier) + one predicated LOP3
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bad) : "f"(fabsf(d)), "f"(0.5f - TB200_TIE_EPS), "r"(bit));
+    return (uint32_t)__float_as_int(r) + (U8 ? (uint32_t)e.out_zero : 0u);
 }
 
-// per-channel operands of the fast path: (m, bias)
-__device__ __forceinline__ int requant_auto(int32_t acc, int oc, const EpiParams& e)
+// Four consecutive channels -> one packed 32-bit word (3 PRMT).  `bad` receives bits (bit0 << j) for guarded elements.
+template <bool U8>
+__device__ __forceinline__ uint32_t requant_fast4(const int32_t (&acc)[4], const EpiParams& e, const float (&m)[4], const int32_t (&b)[4],
+                                                  uint32_t& bad, uint32_t bit0)
 {
-    if (!e.fast_ok) return requant(acc, oc, e);
-    return requant_fast(acc, oc, e, __ldg(e.fast_m + oc), (e.has_bias && !e.is_uint8) ? __ldg(e.bias + oc) : 0);
+    const uint32_t r0 = requant_fast_bits<U8>(acc[0], e, m[0], b[0], bad, bit0);
+    const uint32_t r1 = requant_fast_bits<U8>(acc[1], e, m[1], b[1], bad, bit0 << 1);
+    const uint32_t r2 = requant_fast_bits<U8>(acc[2], e, m[2], b[2], bad, bit0 << 2);
+    const uint32_t r3 = requant_fast_bits<U8>(acc[3], e, m[3], b[3], bad, bit0 << 3);
+    return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
+}
+
+// Replace byte j of `word` by the exact result (rare path: ~2.4e-4 of the elements).
+__device__ __forceinline__ uint32_t requant_fix_byte(uint32_t word, int j, int32_t acc, int oc, const EpiParams& e)
+{
+    const uint32_t q = (uint32_t)requant(acc, oc, e) & 0xffu;
+    return (word & ~(0xffu << (8 * j))) | (q << (8 * j));
+}
+
+// Generic entry for kernels that handle one word (4 channels oc0..oc0+3) at a time with constants in global memory.
+// Pad channels (>= oc_limit) have m = 0, b = 0 in fast_par and therefore produce 0.
+template <bool U8>
+__device__ __forceinline__ uint32_t requant_word(const int32_t (&acc)[4], int oc0, int oc_limit, const EpiParams& e)
+{
+    if (!e.fast_ok)
+    {
+        uint32_t w = 0;
+#pragma unroll 1
+        for (int j = 0; j < 4; j++)
+            if (oc0 + j < oc_limit) w |= ((uint32_t)requant(acc[j], oc0 + j, e) & 0xffu) << (8 * j);
+        return w;
+    }
+    float m[4];
+    int32_t b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float2 p = __ldg(e.fast_par + oc0 + j);
+        m[j] = p.x, b[j] = __float_as_int(p.y);
+    }
+    uint32_t bad = 0;
+    uint32_t w = requant_fast4<U8>(acc, e, m, b, bad, 1u);
+    if (U8)
+    {
+        // pad lanes of uint8 tensors must hold 0 (not the zero point): mask them
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (oc0 + j >= oc_limit) w &= ~(0xffu << (8 * j)), bad &= ~(1u << j);
+    }
+    if (bad)
+    {
+#pragma unroll 1
+        for (int j = 0; j < 4; j++)
+            if ((bad >> j) & 1u) w = requant_fix_byte(w, j, acc[j], oc0 + j, e);
+    }
+    return w;
 }
 
 __device__ __forceinline__ int dp4a_s8(int a, int b, int c) { return __dp4a(a, b, c); }

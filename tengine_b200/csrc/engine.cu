@@ -403,7 +403,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             blobs[li].scale_off = wtotal;
             wtotal += align_up((size_t)tout.cp * 4, 256);
             blobs[li].fast_off = wtotal;
-            wtotal += align_up((size_t)tout.cp * 4, 256);
+            wtotal += align_up((size_t)tout.cp * 8, 256);
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
@@ -472,7 +472,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             }
             int32_t* b = (int32_t*)(img.data() + blobs[li].bias_off);
             float* sc = (float*)(img.data() + blobs[li].scale_off);
-            float* fm = (float*)(img.data() + blobs[li].fast_off);
+            float* fm = (float*)(img.data() + blobs[li].fast_off); // float2 per channel: (multiplier | bias term, bias bits)
             const bool fc = L.op == TB200_OP_FC;
             for (int o = 0; o < tout.cp; o++)
             {
@@ -482,12 +482,16 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 {
                     // the bias term in real units, rounded exactly as the reference rounds it
                     const float S = tin.d.scale * L.weight_scales[0];
-                    fm[o] = (L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0];
+                    fm[2 * o] = (o >= OC) ? 0.f : ((L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0]);
+                    fm[2 * o + 1] = 0.f;
                 }
-                else if (fc)
-                    fm[o] = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
                 else
-                    fm[o] = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
+                {
+                    if (o >= OC) fm[2 * o] = 0.f;
+                    else if (fc) fm[2 * o] = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
+                    else fm[2 * o] = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
+                    memcpy(&fm[2 * o + 1], &b[o], 4);
+                }
             }
         }
         CUDA_OK(cudaMemcpyAsync(g->w_arena, img.data(), g->w_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -522,7 +526,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.epi = make_epi(L, tin.d, tout.d, fc);
             s.epi.bias = (const int32_t*)(g->w_arena + blobs[li].bias_off);
             s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
-            s.epi.fast_m = (const float*)(g->w_arena + blobs[li].fast_off);
+            s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
             ConvShape& cs = s.cs;
             cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
             if (fc)

@@ -7,12 +7,12 @@
 // (source/device/cpu/op/conv/x86/conv_kernel_x86.c:187-242, 1008-1631, 1796-1893) and of ref_fc_int8
 // (fc/fc_ref.c:209-297): with NHWC activations a 1x1 convolution IS this GEMM, no im2col pass exists.
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 576 threads):
 //   warp 0    : TMA producer  (cp.async.bulk.tensor.2d -> 128B/64B/32B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1    : MMA issuer    (one elected lane: tcgen05.mma.cta_group::1.kind::i8, 128 x BN x 32 per instruction;
 //                              tcgen05.commit releases smem stages / publishes the accumulator)
-//   warps 2-9 : epilogue      (two warps per TMEM lane quarter: tcgen05.ld 32x32b -> registers -> requant_fast ->
-//                              int8 -> padded smem tile -> coalesced 16-byte global stores)
+//   warps 2-17: epilogue      (four warps per TMEM lane quarter, 16-column chunks dealt round-robin: tcgen05.ld 32x32b ->
+//                              registers -> requant_fast4 -> int8 -> padded smem tile -> coalesced 16-byte global stores)
 // Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
 // These layers are HBM-bound (K is 32..1024): the budget is ~8-10 issued instructions per output element, which is
 // why the epilogue uses the ~10-instruction requant_fast (common.cuh) and keeps per-channel constants in smem.
@@ -24,8 +24,9 @@
 namespace tb200 {
 
 static constexpr int BLOCK_M = 128;
-static constexpr int GEMM_THREADS = 320;
-static constexpr int EPI_THREADS = 256;
+static constexpr int EPI_WARPS = 16; // four per TMEM lane quarter
+static constexpr int EPI_THREADS = EPI_WARPS * 32;
+static constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 static constexpr int OUT_PAD = 16; // row padding of the staged output tile (bank-conflict-free 16-byte accesses)
 static constexpr int MAX_STAGES = 8;
 
@@ -98,6 +99,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, rows of `swizzle` bytes, 8-row groups `8*swizzle` bytes apart
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < g.stages; s++) mbar_init(&ctl->full[s], 1), mbar_init(&ctl->empty[s], 1);
-        for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], 8);
+        for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2)
@@ -240,12 +261,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     else
     {
-        // ===================== epilogue (warps 2..9) =====================
-        const int q = warp & 3;           // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
-        const int half = (warp - 2) >> 2; // the two warps of a quarter take alternate 16-column chunks
-        const int et = threadIdx.x - 64;  // 0..255
+        // ===================== epilogue (warps 2..17) =====================
+        const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
+        const int split = (warp - 2) >> 2; // 0..3: which of the quarter's four warps
+        const int et = threadIdx.x - 64;   // 0..EPI_THREADS-1
         const int opitch = g.block_n + OUT_PAD;
         const int vec_per_row = g.block_n >> 4;
+        const uint32_t par_s = smem_u32(epi_par), ost_s = smem_u32(ostage);
         int as = 0;
         uint32_t aphase = 0;
         int loaded_n0 = -1;
@@ -255,17 +277,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int n0 = (int)(tile % g.n_tiles) * g.block_n;
             if (n0 != loaded_n0)
             {
-                // per-channel fast-path constants of this N tile -> smem (previous tile's readers passed barrier B)
+                // per-channel fast-path constants (m, bias) of this N tile -> smem; pad / overhanging channels get (0, 0)
                 for (int c = et; c < g.block_n; c += EPI_THREADS)
                 {
                     const int oc = n0 + c;
-                    float2 v = make_float2(0.f, 0.f);
-                    if (oc < g.ocp)
-                    {
-                        v.x = e.fast_ok ? __ldg(e.fast_m + oc) : 0.f;
-                        v.y = __int_as_float((e.has_bias && !e.is_uint8) ? __ldg(e.bias + oc) : 0);
-                    }
-                    epi_par[c] = v;
+                    sts_f2(par_s + c * 8, (oc < g.ocp && e.fast_ok) ? __ldg(e.fast_par + oc) : make_float2(0.f, 0.f));
                 }
                 loaded_n0 = n0;
             }
@@ -274,34 +290,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             epi_bar_sync(1); // A: constants visible; everybody finished copying the previous tile out of `ostage`
             const int rloc = q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.block_n);
-            uint8_t* srow = ostage + (size_t)rloc * opitch;
-            for (int c = half * 16; c < g.block_n; c += 32)
+            const uint32_t srow = ost_s + (uint32_t)(rloc * opitch);
+            for (int c = split * 16; c < g.block_n; c += 16 * (EPI_WARPS / 4))
             {
                 uint32_t v[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld_wait();
                 uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
+                if (e.fast_ok)
                 {
-                    uint32_t packed = 0;
+                    uint32_t bad = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++)
+                    for (int j = 0; j < 4; j++)
                     {
-                        const int cc = c + j * 4 + t;
-                        const int oc = n0 + cc;
-                        int qv = 0;
-                        if (oc < g.oc)
-                        {
-                            const float2 par = epi_par[cc];
-                            qv = e.fast_ok ? requant_fast((int32_t)v[j * 4 + t], oc, e, par.x, __float_as_int(par.y))
-                                           : requant((int32_t)v[j * 4 + t], oc, e);
-                        }
-                        packed |= (uint32_t)qv << (8 * t);
+                        const float4 p01 = lds_f4(par_s + (c + j * 4) * 8);
+                        const float4 p23 = lds_f4(par_s + (c + j * 4 + 2) * 8);
+                        const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
+                        const int32_t b4[4] = {__float_as_int(p01.y), __float_as_int(p01.w), __float_as_int(p23.y), __float_as_int(p23.w)};
+                        const int32_t a4[4] = {(int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3]};
+                        w[j] = requant_fast4<false>(a4, e, m4, b4, bad, 1u << (4 * j));
                     }
-                    w[j] = packed;
+                    if (bad)
+                    {
+                        // rare (2.4e-4 of the elements): exact recomputation; fully unrolled so v[] stays in registers
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, (int32_t)v[k], n0 + c + k, e);
+                    }
                 }
-                *reinterpret_cast<uint4*>(srow + c) = make_uint4(w[0], w[1], w[2], w[3]);
+                else
+                {
+                    // degenerate scales: literal arithmetic for every element
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        if ((k & 3) == 0) w[k >> 2] = 0;
+                        if (n0 + c + k < g.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], n0 + c + k, e) & 0xffu) << (8 * (k & 3));
+                    }
+                }
+                sts_u4(srow + c, w[0], w[1], w[2], w[3]);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -314,8 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             {
                 const int r = vi / vec_per_row, cv = vi - r * vec_per_row;
                 if (m0 + r < g.m && n0 + cv * 16 < g.ocp)
-                    *reinterpret_cast<uint4*>(out + (size_t)(m0 + r) * g.ldo + n0 + cv * 16) =
-                        *reinterpret_cast<const uint4*>(ostage + (size_t)r * opitch + cv * 16);
+                    *reinterpret_cast<uint4*>(out + (size_t)(m0 + r) * g.ldo + n0 + cv * 16) = lds_u4(ost_s + (uint32_t)(r * opitch + cv * 16));
             }
         }
     }

@@ -73,22 +73,15 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restr
 #pragma unroll
     for (int j = 0; j < OCT; j += 4)
     {
-        unsigned packed = 0;
+        int32_t a4[4];
 #pragma unroll
         for (int t = 0; t < 4; t++)
         {
-            const int oc = oc0 + j + t;
-            int q = 0;
-            if (oc < s.oc)
-            {
-                int a = acc[j + t];
-                if (U8) // sum (x-zx)(w-zw) = Sxw - zw*Sx - zx*Sw + cnt*zx*zw   (cnt counts REAL channels only)
-                    a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.cg * e.in_zero * e.w_zero;
-                q = requant_auto(a, oc, e);
-            }
-            packed |= (unsigned)q << (8 * t);
+            a4[t] = acc[j + t];
+            if (U8) // sum (x-zx)(w-zw) = Sxw - zw*Sx - zx*Sw + cnt*zx*zw   (cnt counts REAL channels only)
+                a4[t] = a4[t] - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.cg * e.in_zero * e.w_zero;
         }
-        *reinterpret_cast<unsigned*>(op + j) = packed;
+        *reinterpret_cast<unsigned*>(op + j) = requant_word<U8>(a4, oc0 + j, s.oc, e);
     }
 }
 
@@ -140,15 +133,7 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict_
             }
         }
     }
-    unsigned packed = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-    {
-        const int c = c4 * 4 + t;
-        const int q = (c < s.oc) ? requant_auto(acc[t], c, e) : 0;
-        packed |= (unsigned)q << (8 * t);
-    }
-    reinterpret_cast<unsigned*>(out + (size_t)pix * s.ocp)[c4] = packed;
+    reinterpret_cast<unsigned*>(out + (size_t)pix * s.ocp)[c4] = requant_word<U8>(acc, c4 * 4, s.oc, e);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -213,31 +198,49 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
                 for (int j = 0; j < 4; j++) acc[t][j] = dp4a_s8(xv[t * S + kw], wj[kh * 3 + kw][j], acc[t][j]);
     }
 
+    uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
+    if (!e.fast_ok)
+    {
+#pragma unroll 1
+        for (int t = 0; t < TW; t++)
+            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
+        return;
+    }
     float m[4];
-    int b[4];
+    int32_t b[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const int c = c4 * 4 + j;
-        m[j] = e.fast_ok ? __ldg(e.fast_m + c) : 0.f;
-        b[j] = e.has_bias ? __ldg(e.bias + c) : 0;
+        const float2 p = __ldg(e.fast_par + c4 * 4 + j); // pad channels: (0, 0) -> output byte 0
+        m[j] = p.x, b[j] = __float_as_int(p.y);
     }
-    uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
+    uint32_t bad = 0;
+    uint32_t w[TW];
+#pragma unroll
+    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    if (bad)
+    {
+#pragma unroll 1
+        for (int i = 0; i < 4 * TW; i++)
+            if ((bad >> i) & 1u)
+            {
+                // dynamic register-array indexing would spill: select with a small unrolled switch
+                int32_t a = 0;
+                uint32_t word = 0;
+#pragma unroll
+                for (int t = 0; t < TW; t++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (i == t * 4 + j) a = acc[t][j], word = w[t];
+                word = requant_fix_byte(word, i & 3, a, c4 * 4 + (i & 3), e);
+#pragma unroll
+                for (int t = 0; t < TW; t++)
+                    if ((i >> 2) == t) w[t] = word;
+            }
+    }
 #pragma unroll
     for (int t = 0; t < TW; t++)
-    {
-        if (ow0 + t >= s.ow) break;
-        unsigned packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-        {
-            const int c = c4 * 4 + j;
-            int q = 0;
-            if (c < s.oc) q = e.fast_ok ? requant_fast(acc[t][j], c, e, m[j], b[j]) : requant(acc[t][j], c, e);
-            packed |= (unsigned)q << (8 * j);
-        }
-        reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = packed;
-    }
+        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -296,21 +299,14 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const uint8_t* __restric
 #pragma unroll
     for (int j = 0; j < OCT; j += 4)
     {
-        unsigned packed = 0;
+        int32_t a4[4];
 #pragma unroll
         for (int t = 0; t < 4; t++)
         {
-            const int oc = oc0 + j + t;
-            int q = 0;
-            if (oc < s.oc)
-            {
-                int a = acc[j + t];
-                if (U8) a = a - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.c * e.in_zero * e.w_zero;
-                q = requant_auto(a, oc, e);
-            }
-            packed |= (unsigned)q << (8 * t);
+            a4[t] = acc[j + t];
+            if (U8) a4[t] = a4[t] - e.w_zero * sx_sum - e.in_zero * sw_sum[j + t] + taps * s.c * e.in_zero * e.w_zero;
         }
-        *reinterpret_cast<unsigned*>(op + j) = packed;
+        *reinterpret_cast<unsigned*>(op + j) = requant_word<U8>(a4, oc0 + j, s.oc, e);
     }
 }
 
