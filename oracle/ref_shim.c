@@ -28,6 +28,7 @@
 #include "operator/prototype/eltwise_param.h"
 #include "operator/prototype/concat_param.h"
 #include "operator/prototype/upsample_param.h"
+#include "operator/op.h"
 
 #include "../include/tengine_b200.h"
 
@@ -230,8 +231,10 @@ static int build_graph(struct built* B, const tb200_tensor_desc* tensors, int nu
             struct pool_param* p = (struct pool_param*)pm;
             p->pool_method = L->pool_method, p->global = L->pool_global, p->caffe_flavor = L->caffe_flavor;
             p->kernel_h = L->kernel_h, p->kernel_w = L->kernel_w, p->stride_h = L->stride_h, p->stride_w = L->stride_w;
-            p->pad_h0 = p->pad_h0_org = L->pad_h0, p->pad_h1 = p->pad_h1_org = L->pad_h1;
-            p->pad_w0 = p->pad_w0_org = L->pad_w0, p->pad_w1 = p->pad_w1_org = L->pad_w1;
+            p->pad_h0 = L->pad_h0, p->pad_h1 = L->pad_h1, p->pad_w0 = L->pad_w0, p->pad_w1 = L->pad_w1;
+            /* the *_org values infer_shape starts from (pooling.c:68-92): caffe_flavor 2 splits pad_org into (org/2, org-org/2) */
+            p->pad_h0_org = p->pad_h1_org = (L->caffe_flavor == 2) ? L->pad_h0 + L->pad_h1 : L->pad_h0;
+            p->pad_w0_org = p->pad_w1_org = (L->caffe_flavor == 2) ? L->pad_w0 + L->pad_w1 : L->pad_w0;
             break;
         }
         case TB200_OP_RELU: ((struct relu_param*)pm)->negative_slope = L->negative_slope; break;
@@ -364,3 +367,54 @@ SHIM_API int ref_shim_save_tmfile(const tb200_tensor_desc* tensors, int num_tens
 }
 
 SHIM_API const char* ref_shim_version(void) { return get_tengine_version(); }
+
+/* Print op + parameters of every non-const node of a tmfile (used to mirror the reference's benchmark graphs in
+ * tengine_b200/workloads.py). */
+SHIM_API int ref_shim_describe_tmfile(const char* fname)
+{
+    if (!g_inited)
+    {
+        if (init_tengine() != 0) return -100;
+        g_inited = 1;
+    }
+    graph_t graph = create_graph(NULL, "tengine", fname);
+    if (!graph) return -1;
+    struct graph* g = (struct graph*)graph;
+    infer_ir_graph_shape(g);
+    for (int i = 0; i < g->node_num; i++)
+    {
+        struct node* n = g->node_list[i];
+        if (n->op.type == OP_CONST) continue;
+        struct tensor* o = g->tensor_list[n->output_tensors[0]];
+        printf("%d %s out[%d,%d,%d,%d] in:", i, get_node_op(n), o->dims[0], o->dims[1], o->dims[2], o->dims[3]);
+        for (int k = 0; k < n->input_num; k++)
+        {
+            struct tensor* t = g->tensor_list[n->input_tensors[k]];
+            if (t->tensor_type != TENSOR_TYPE_CONST) printf(" n%d", t->producer);
+        }
+        if (n->op.type == OP_CONV)
+        {
+            struct conv_param* p = (struct conv_param*)n->op.param_mem;
+            printf(" k%dx%d s%d,%d p%d,%d,%d,%d d%d g%d act%d oc%d", p->kernel_h, p->kernel_w, p->stride_h, p->stride_w, p->pad_h0, p->pad_h1,
+                   p->pad_w0, p->pad_w1, p->dilation_h, p->group, p->activation, p->output_channel);
+        }
+        else if (n->op.type == OP_POOL)
+        {
+            struct pool_param* p = (struct pool_param*)n->op.param_mem;
+            printf(" method%d k%dx%d s%d,%d p%d,%d,%d,%d porg%d,%d,%d,%d global%d caffe%d", p->pool_method, p->kernel_h, p->kernel_w, p->stride_h,
+                   p->stride_w, p->pad_h0, p->pad_h1, p->pad_w0, p->pad_w1, p->pad_h0_org, p->pad_h1_org, p->pad_w0_org, p->pad_w1_org,
+                   p->global, p->caffe_flavor);
+        }
+        else if (n->op.type == OP_RELU)
+            printf(" slope%g", ((struct relu_param*)n->op.param_mem)->negative_slope);
+        else if (n->op.type == OP_ELTWISE)
+            printf(" type%d", ((struct eltwise_param*)n->op.param_mem)->type);
+        else if (n->op.type == OP_UPSAMPLE)
+            printf(" scale%g", ((struct upsample_param*)n->op.param_mem)->scale);
+        else if (n->op.type == OP_CONCAT)
+            printf(" axis%d", ((struct concat_param*)n->op.param_mem)->axis);
+        printf("\n");
+    }
+    destroy_graph(graph);
+    return 0;
+}

@@ -385,7 +385,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         else if (L.op == TB200_OP_CONCAT)
         {
             if (L.axis != 1) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: concat axis %d", li, L.axis));
-            kind[li] = K_CONCAT_PART;
+            kind[li] = (L.num_inputs == 1) ? K_COPY : K_CONCAT_PART; // concat_kernel_ref_int8.c:45-56: one input is a plain copy
         }
         else if (L.op == TB200_OP_UPSAMPLE)
             kind[li] = K_UPSAMPLE;
@@ -583,7 +583,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.bytes = (long long)tin.nhwc_bytes;
             if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: pointwise shape mismatch", li));
         }
-        else if (L.op == TB200_OP_CONCAT)
+        else if (L.op == TB200_OP_CONCAT && L.num_inputs > 1)
         {
             int coff = 0;
             for (int k = 0; k < L.num_inputs; k++)
@@ -604,7 +604,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.n = N, s.h = H, s.w_ = W, s.cp_in = tin.cp, s.scale = L.up_scale;
             if (OH != H * L.up_scale || OW != W * L.up_scale) return bail(fail(TB200_ERR_INVALID, "layer %d: upsample shape", li));
         }
-        else if (L.op == TB200_OP_IDENTITY)
+        else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT)
         {
             s.bytes = (long long)tin.nhwc_bytes;
             if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));

@@ -100,10 +100,22 @@ class GraphDef:
         if global_pool or (kh == h and kw == w and not any(p)):
             kh, kw, sh, sw, p, oh, ow, global_pool = h, w, 1, 1, (0, 0, 0, 0), 1, 1, True
         else:
-            # operator/prototype/pooling_param.h:59-82 calc_output_size (caffe 0) + calc_real_pads
-            oh = 1 + (h - kh + 2 * p[0]) // sh
-            ow = 1 + (w - kw + 2 * p[2]) // sw
-            p = (p[0], max((oh - 1) * sh + kh - h, 0) - p[0], p[2], max((ow - 1) * sw + kw - w, 0) - p[2])
+            # operator/prototype/pooling_param.h:59-105 calc_output_size + calc_real_pads; `pad` is pad_*_org
+            def out_dim(i, k, s_, po):
+                if caffe_flavor == 1:
+                    o = 2 + (i - k + 2 * po - 1) // s_
+                    if po > 0 and (o - 1) * s_ >= i + po:
+                        o -= 1
+                    return o
+                if caffe_flavor == 2:
+                    return 1 + (i - k + po) // s_
+                return 1 + (i - k + 2 * po) // s_
+
+            oh, ow = out_dim(h, kh, sh, p[0]), out_dim(w, kw, sw, p[2])
+            if caffe_flavor == 2:
+                p = (p[0] // 2, p[0] - p[0] // 2, p[2] // 2, p[2] - p[2] // 2)
+            else:
+                p = (p[0], max((oh - 1) * sh + kh - h, 0) - p[0], p[2], max((ow - 1) * sw + kw - w, 0) - p[2])
         src = self.tensors[x]
         out = self.add_tensor((n, c, oh, ow), src["scale"] if out_scale is None else out_scale,
                               src["zero_point"] if out_zero is None else out_zero)

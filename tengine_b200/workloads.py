@@ -108,27 +108,28 @@ class QuantBuilder:
         so, zo = self._act_q(a)
         return _H(self.g.fc(x.tid, wq, bq, ws, so, zo, weight_zero=wz), a)
 
-    def pool(self, x, method, kernel, stride, pad=0, global_pool=False):
+    def pool(self, x, method, kernel, stride, pad=0, global_pool=False, caffe_flavor=0):
+        """`pad` is the reference's pad_*_org; the real (possibly asymmetric) pads come from GraphDef.pool()."""
         F = self.torch.nn.functional
-        if global_pool:
+        tid = self.g.pool(x.tid, method, kernel, stride, pad, out_scale=1.0, out_zero=0, global_pool=global_pool,
+                          caffe_flavor=caffe_flavor)
+        L = self.g.layers[-1]
+        if L["pool_global"]:
             a = x.act.mean(dim=(2, 3), keepdim=True) if method == abi.POOL_AVG else x.act.amax(dim=(2, 3), keepdim=True)
         else:
-            p = (pad, pad, pad, pad) if np.isscalar(pad) else pad
-            # reference asymmetric pad: extra rows/cols at the bottom/right, never counted (caffe_flavor 0)
-            n, c, h, w = x.act.shape
-            oh = 1 + (h - kernel + 2 * p[0]) // stride
-            ow = 1 + (w - kernel + 2 * p[2]) // stride
-            ph1 = max((oh - 1) * stride + kernel - h - p[0], 0)
-            pw1 = max((ow - 1) * stride + kernel - w - p[2], 0)
+            # calibration only: windows clipped to the image (extra bottom/right rows never contribute)
+            ph0, ph1, pw0, pw1 = L["pad_h0"], L["pad_h1"], L["pad_w0"], L["pad_w1"]
             if method == abi.POOL_MAX:
-                xp = F.pad(x.act, (p[2], pw1, p[0], ph1), value=float("-inf"))
+                xp = F.pad(x.act, (pw0, pw1, ph0, ph1), value=float("-inf"))
                 a = F.max_pool2d(xp, kernel, stride)
             else:
-                xp = F.pad(x.act, (p[2], pw1, p[0], ph1), value=0.0)
-                ones = F.pad(self.torch.ones_like(x.act), (p[2], pw1, p[0], ph1), value=0.0)
+                xp = F.pad(x.act, (pw0, pw1, ph0, ph1), value=0.0)
+                ones = F.pad(self.torch.ones_like(x.act), (pw0, pw1, ph0, ph1), value=0.0)
                 a = F.avg_pool2d(xp, kernel, stride) / F.avg_pool2d(ones, kernel, stride).clamp_min(1e-9)
+            oh, ow = self.g.dims(tid)[2:]
+            a = a[:, :, :oh, :ow]
         so, zo = self._act_q(a)
-        tid = self.g.pool(x.tid, method, kernel, stride, pad, out_scale=so, out_zero=zo, global_pool=global_pool)
+        self.g.tensors[tid]["scale"], self.g.tensors[tid]["zero_point"] = float(so), int(zo)
         return _H(tid, a)
 
     def relu(self, x, negative_slope=0.0):
@@ -145,6 +146,11 @@ class QuantBuilder:
         a = self.torch.cat([x.act for x in xs], dim=1)
         so, zo = self._act_q(a)
         return _H(self.g.concat([x.tid for x in xs], so, zo), a)
+
+    def concat1(self, x):
+        """Single-input Concat (a plain copy in the reference, concat_kernel_ref_int8.c:45-56)."""
+        src = self.g.tensors[x.tid]
+        return _H(self.g.concat([x.tid], src["scale"], src["zero_point"]), x.act)
 
     def upsample(self, x, scale):
         a = self.torch.nn.functional.interpolate(x.act, scale_factor=scale, mode="nearest")
@@ -212,3 +218,59 @@ def tiny_net(data_type=abi.DT_INT8, batch=2, seed=7):
     g = b.pool(l, abi.POOL_AVG, 10, 1, global_pool=True)
     f = b.fc(g, 10)
     return b.finish([f, l]), b
+
+
+def resnet50(data_type=abi.DT_UINT8, batch=1, res=224, seed=1234, width=1.0, classes=1000, blocks=(3, 4, 6, 3)):
+    """ResNet-50 as in benchmark/models/resnet50_benchmark.tmfile (Caffe layout): 7x7 s2 stem with fused ReLU, 3x3 s2
+    max-pool (caffe_flavor 1 -> real pads 0,1,0,1), bottlenecks whose projection / first 1x1 carry the stride, Eltwise-sum
+    followed by a STANDALONE ReLU node (each re-quantises), global average pool, FC 2048->1000 (Softmax stays on the CPU)."""
+    b = QuantBuilder(data_type, batch, 3, res, res, seed)
+    ch = lambda c: max(16, int(c * width))
+    x = b.conv(b.input, ch(64), 7, stride=2, pad=3, activation=0)
+    x = b.pool(x, abi.POOL_MAX, 3, 2, 0, caffe_flavor=1)
+    for stage, nblk in enumerate(blocks):
+        mid, out = ch(64 << stage), ch(256 << stage)
+        for i in range(nblk):
+            stride = 2 if (i == 0 and stage > 0) else 1
+            y = b.conv(x, mid, 1, stride=stride, activation=0)
+            y = b.conv(y, mid, 3, pad=1, activation=0)
+            y = b.conv(y, out, 1, activation=-1)
+            if i == 0:
+                sc = b.conv(x, out, 1, stride=stride, activation=-1)
+                x = b.add(sc, y)
+            else:
+                x = b.add(x, y)
+            x = b.relu(x)
+    x = b.pool(x, abi.POOL_AVG, b.g.dims(x.tid)[2], 1, global_pool=True, caffe_flavor=1)
+    x = b.fc(x, classes)
+    return b.finish([x]), b
+
+
+def yolov3_tiny(data_type=abi.DT_UINT8, batch=1, res=416, seed=1234, width=1.0, head=255):
+    """YOLOv3-tiny as in benchmark/models/yolov3_tiny_benchmark.tmfile: 3x3 convs WITHOUT fused activation, each followed
+    by a standalone leaky ReLU (slope 0.1), 2x2 max-pools with caffe_flavor 2 / pad_org 1 (real pads 0,1,0,1; the last one
+    has stride 1), a single-input Concat, nearest Upsample x2, a two-input Concat (384 ch) and two 1x1 heads of 255 channels
+    followed by Dropout (identity)."""
+    b = QuantBuilder(data_type, batch, 3, res, res, seed)
+    ch = lambda c: max(8, int(c * width))
+
+    def cbl(x, oc, k):
+        return b.relu(b.conv(x, oc, k, pad=k // 2, activation=-1), negative_slope=0.1)
+
+    x = b.input
+    feats = []
+    for i, oc in enumerate((16, 32, 64, 128, 256, 512)):
+        x = cbl(x, ch(oc), 3)
+        feats.append(x)
+        x = b.pool(x, abi.POOL_MAX, 2, 2 if i < 5 else 1, 1, caffe_flavor=2)
+    x = cbl(x, ch(1024), 3)
+    x = cbl(x, ch(256), 1)
+    route = b.concat1(x)
+    y = cbl(route, ch(128), 1)
+    y = b.upsample(y, 2)
+    y = b.concat([y, feats[4]])
+    y = cbl(y, ch(256), 3)
+    big = cbl(x, ch(512), 3)
+    o26 = b.identity(b.conv(y, head, 1, activation=-1))
+    o13 = b.identity(b.conv(big, head, 1, activation=-1))
+    return b.finish([o26, o13]), b
