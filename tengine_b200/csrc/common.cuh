@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t requant_word(const int32_t (&acc)[4], int oc
     if (!e.fast_ok)
     {
         uint32_t w = 0;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; j++)
             if (oc0 + j < oc_limit) w |= ((uint32_t)requant(acc[j], oc0 + j, e) & 0xffu) << (8 * j);
         return w;
@@ -211,7 +211,7 @@ __device__ __forceinline__ uint32_t requant_word(const int32_t (&acc)[4], int oc
     }
     if (bad)
     {
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; j++)
             if ((bad >> j) & 1u) w = requant_fix_byte(w, j, acc[j], oc0 + j, e);
     }

@@ -1,0 +1,157 @@
+// dw_tma.cu -- depthwise 3x3 int8 (stride 1 / 2), the MobileNet depthwise path, with TMA-staged input tiles.
+//
+// One CTA = 32 channels x R output rows x up to 128/R... output pixels: ONE elected thread issues ONE 4-D
+// cp.async.bulk.tensor load (box = 32 channels x cols x rows x 1 image; out-of-bounds coordinates are zero-filled by
+// the TMA unit, which IS the convolution's zero padding), everybody waits on the mbarrier, then each thread computes
+// 4 channels x TW consecutive output pixels from shared memory with one dp4a per MAC (one-hot weight bytes) and the
+// fused requantising epilogue.  No per-thread global loads, no boundary predicates, every input byte crosses L2->SM
+// once per CTA.  Several CTAs per SM overlap one CTA's TMA latency with the others' arithmetic.
+// Takes the role of convdw3x3s1_int8_sse / convdw3x3s2_int8_sse (source/device/cpu/op/conv/x86/conv_dw_hcl_x86.c:97-445).
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tb200 {
+
+static constexpr int DW_THREADS = 128;
+static constexpr int DW_CH = 32; // channels per CTA (8 words)
+
+template <int TW, int S>
+__global__ void __launch_bounds__(DW_THREADS, 6)
+    conv_dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out,
+                          const ConvShape s, const __grid_constant__ EpiParams e, const int rows_per_cta, const int gpr, const int tile_cols,
+                          const int tile_rows)
+{
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int chunk = blockIdx.x;           // 32-channel chunk
+    const int oh0 = blockIdx.y * rows_per_cta;
+    const int n = blockIdx.z;
+    const int word = threadIdx.x & 7;       // 4-channel word inside the chunk
+    const int pg = threadIdx.x >> 3;        // pixel group 0..15
+    const int r = pg / gpr, gi = pg - r * gpr;
+    const int oh = oh0 + r, ow0 = gi * TW;
+    const int c4 = chunk * 8 + word;        // word index in the full channel dimension
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_expect_tx(&bar, (uint32_t)(tile_rows * tile_cols * DW_CH));
+        tma_load_4d(&tmap_in, &bar, dw_smem, chunk * DW_CH, -s.pw0, oh0 * S - s.ph0, n);
+    }
+    // weights / epilogue constants while the tile is in flight
+    const bool active = (r < rows_per_cta) && (oh < s.oh) && (ow0 < s.ow) && (c4 * 4 < s.cp);
+    int wj[9][4];
+    float m[4];
+    int32_t b[4];
+    if (active)
+    {
+#pragma unroll
+        for (int t = 0; t < 9; t++)
+        {
+            const unsigned wv = __ldg(reinterpret_cast<const unsigned*>(wgt + (size_t)t * s.cp) + c4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) wj[t][j] = (int)(wv & (0xffu << (8 * j)));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const float2 p = e.fast_ok ? __ldg(e.fast_par + c4 * 4 + j) : make_float2(0.f, 0.f);
+            m[j] = p.x, b[j] = __float_as_int(p.y);
+        }
+    }
+    mbar_wait(&bar, 0);
+    if (!active) return;
+
+    int acc[TW][4];
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[t][j] = 0;
+    constexpr int COLS = (TW - 1) * S + 3;
+    const uint32_t base = smem_u32(dw_smem) + (uint32_t)(((r * S) * tile_cols + ow0 * S) * DW_CH + word * 4);
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+    {
+        int xv[COLS];
+#pragma unroll
+        for (int col = 0; col < COLS; col++)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xv[col]) : "r"(base + (uint32_t)((kh * tile_cols + col) * DW_CH)));
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[t][j] = dp4a_s8(xv[t * S + kw], wj[kh * 3 + kw][j], acc[t][j]);
+    }
+
+    uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
+    if (!e.fast_ok)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
+        return;
+    }
+    uint32_t bad = 0;
+    uint32_t w[TW];
+#pragma unroll
+    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    if (bad)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((bad >> (t * 4 + j)) & 1u) w[t] = requant_fix_byte(w[t], j, acc[t][j], c4 * 4 + j, e);
+    }
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+}
+
+// Plan: tile geometry + the 4-D tensor map (C, W, H, N) of the input.  Returns 0, or <0 when this layer must use the
+// generic depthwise kernel (uint8, stride > 2, very wide rows ...).
+int dw_plan_create(DwPlan* p, const void* in, const ConvShape& s, const EpiParams& e)
+{
+    p->valid = 0;
+    if (e.is_uint8 || s.kh != 3 || s.kw != 3 || s.dh != 1 || s.dw != 1 || s.sh != s.sw || (s.sh != 1 && s.sh != 2)) return -1;
+    const int S = s.sh;
+    p->tw = (S == 1) ? 8 : 4;
+    p->gpr = (s.ow + p->tw - 1) / p->tw;
+    if (p->gpr > 16) return -1; // rows wider than 16 pixel groups: generic kernel
+    p->rows_per_cta = 16 / p->gpr;
+    if (p->rows_per_cta > s.oh) p->rows_per_cta = s.oh;
+    p->tile_cols = (p->gpr * p->tw - 1) * S + 3;
+    p->tile_rows = (p->rows_per_cta - 1) * S + 3;
+    if (p->tile_cols > 256 || p->tile_rows > 256) return -1;
+    p->smem_bytes = p->tile_rows * p->tile_cols * DW_CH;
+    if (p->smem_bytes > 48 * 1024) return -1;
+    const uint64_t dims[4] = {(uint64_t)s.cp, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
+    const uint64_t strides[3] = {(uint64_t)s.cp, (uint64_t)s.w * s.cp, (uint64_t)s.h * s.w * s.cp};
+    const uint32_t box[4] = {(uint32_t)DW_CH, (uint32_t)p->tile_cols, (uint32_t)p->tile_rows, 1u};
+    if (tmap_encode(p->tmap_in, in, 4, dims, strides, box, nullptr, 0) != 0) return -2;
+    p->valid = 1;
+    return 0;
+}
+
+cudaError_t launch_conv_dw_tma(const DwPlan& p, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+{
+    dim3 grid((s.cp + DW_CH - 1) / DW_CH, (s.oh + p.rows_per_cta - 1) / p.rows_per_cta, s.n);
+    CUtensorMap tm;
+    memcpy(&tm, p.tmap_in, sizeof tm);
+    if (s.sh == 1)
+        conv_dw3x3_tma_kernel<8, 1><<<grid, DW_THREADS, p.smem_bytes, st>>>(tm, (const uint8_t*)w, (uint8_t*)out, s, e, p.rows_per_cta, p.gpr,
+                                                                            p.tile_cols, p.tile_rows);
+    else
+        conv_dw3x3_tma_kernel<4, 2><<<grid, DW_THREADS, p.smem_bytes, st>>>(tm, (const uint8_t*)w, (uint8_t*)out, s, e, p.rows_per_cta, p.gpr,
+                                                                            p.tile_cols, p.tile_rows);
+    return cudaGetLastError();
+}
+
+} // namespace tb200

@@ -73,6 +73,7 @@ struct Step
     PointwiseParams pp{};
     EpiParams epi{};
     GemmPlan gemm{};
+    DwPlan dwp{};
     long long bytes = 0; // pointwise / copy
     // concat / layout
     long long npix = 0;
@@ -249,7 +250,9 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_NCHW2NHWC: err = launch_nchw_to_nhwc(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_NHWC2NCHW: err = launch_nhwc_to_nchw(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_CONV_STEM: err = launch_conv_stem(s.in, s.w, s.out, s.cs, s.epi, st); break;
-    case K_CONV_DW: err = launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st); break;
+    case K_CONV_DW:
+        err = s.dwp.valid ? launch_conv_dw_tma(s.dwp, s.w, s.out, s.cs, s.epi, st) : launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st);
+        break;
     case K_CONV_DIRECT: err = launch_conv_direct(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_GEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, g->ctx->num_sms, st); break;
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
@@ -546,6 +549,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
             }
             if (s.kind == K_CONV_STEM) s.in = g->in_nchw_dev[tin.input_index];
+            if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
             if (s.kind == K_GEMM)
             {
                 const long long m = fc ? N : (long long)N * H * W;
@@ -609,7 +613,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.bytes = (long long)tin.nhwc_bytes;
             if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));
         }
-        g->layer_kernel[li] = kStepName[s.kind];
+        g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : kStepName[s.kind];
         g->steps.push_back(s);
     }
     for (size_t i = 0; i < g->output_ids.size(); i++)

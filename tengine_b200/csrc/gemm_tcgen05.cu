@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace tb200 {
 
@@ -29,97 +30,6 @@ static constexpr int EPI_THREADS = EPI_WARPS * 32;
 static constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 static constexpr int OUT_PAD = 16; // row padding of the staged output tile (bank-conflict-free 16-byte accesses)
 static constexpr int MAX_STAGES = 8;
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-    {
-        if (clock64() - t0 > 4000000000LL) __trap(); // ~2 s
-    }
-}
-__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(smem)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v)
-{
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, rows of `swizzle` bytes, 8-row groups `8*swizzle` bytes apart
 // (cute/atom/mma_traits_sm100.hpp: canonical layout ((8,n),2):((swizzle/16,SBO),1), LBO = 1, version 1).
@@ -150,8 +60,10 @@ __host__ __device__ inline uint32_t make_idesc_i8(int block_n, bool a_signed, bo
 
 struct GemmArgs
 {
-    long long m, m_tiles;
+    long long m, m_tiles, num_super;
     int k_blocks, n_tiles, block_n, block_k, stages, swizzle;
+    int mt;     // m-tiles (128 rows each) per accumulator stage
+    int vshift; // log2(block_n / 16) when that is a power of two, else -1
     int oc, ocp, ldo;
     uint32_t idesc;
     uint32_t tmem_cols;
@@ -162,26 +74,67 @@ struct __align__(16) GemmSmemCtl
     uint64_t full[MAX_STAGES], empty[MAX_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    uint32_t pad;
+    uint32_t pad[3];
 };
 
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// 16 accumulator columns of one row -> 16 output bytes staged in shared memory
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, int oc0, int oc_limit,
+                                              const EpiParams& e)
+{
+    uint32_t w[4];
+    if (e.fast_ok)
+    {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const float4 p01 = lds_f4(par_addr + j * 32);
+            const float4 p23 = lds_f4(par_addr + j * 32 + 16);
+            const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
+            const int32_t b4[4] = {__float_as_int(p01.y), __float_as_int(p01.w), __float_as_int(p23.y), __float_as_int(p23.w)};
+            const int32_t a4[4] = {(int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3]};
+            w[j] = requant_fast4<false>(a4, e, m4, b4, bad, 1u << (4 * j));
+        }
+        if (bad)
+        {
+            // rare (2.4e-4 of the elements): exact recomputation; fully unrolled so v[] stays in registers
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, (int32_t)v[k], oc0 + k, e);
+        }
+    }
+    else
+    {
+        // degenerate scales: literal arithmetic for every element
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            if ((k & 3) == 0) w[k >> 2] = 0;
+            if (oc0 + k < oc_limit) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], oc0 + k, e) & 0xffu) << (8 * (k & 3));
+        }
+    }
+    sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                           uint8_t* __restrict__ out, const GemmArgs g, const EpiParams e)
+                           uint8_t* __restrict__ out, const GemmArgs g, const __grid_constant__ EpiParams e)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // operand ring first (1024-byte aligned for the 128B swizzle), control block after it
+    // operand ring first (1024-byte aligned for the 128B swizzle), then the control block, the per-quarter epilogue
+    // constants and the per-quarter output staging tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.block_n * g.block_k;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
     GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(smem + (size_t)g.stages * stage_bytes);
-    float2* epi_par = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(GemmSmemCtl)); // [block_n] (m, bias)
-    uint8_t* ostage = reinterpret_cast<uint8_t*>(epi_par) + (size_t)g.block_n * sizeof(float2);         // [128][block_n + OUT_PAD]
+    const int opitch = g.block_n + OUT_PAD;
+    const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl);   // 4 x [block_n] float2 (m, bias)
+    const uint32_t ost_base = par_base + 4u * (uint32_t)g.block_n * 8u;           // 4 x [mt*32][block_n + OUT_PAD]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long num_tiles = g.m_tiles * g.n_tiles;
+    const int acc_cols = g.mt * g.block_n; // TMEM columns of one accumulator stage
 
     if (threadIdx.x == 0)
     {
@@ -211,17 +164,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
-                const int m0 = (int)((tile / g.n_tiles) * BLOCK_M), n0 = (int)(tile % g.n_tiles) * g.block_n;
-                for (int kb = 0; kb < g.k_blocks; kb++)
+                const long long mt0 = (st / g.n_tiles) * g.mt;
+                const int n0 = (int)(st % g.n_tiles) * g.block_n;
+                for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
                 {
-                    mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    tma_load_2d(&tmap_a, &ctl->full[stage], sa, kb * g.block_k, m0);
-                    tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
-                    if (++stage == g.stages) stage = 0, phase ^= 1;
+                    const int m0 = (int)((mt0 + i) * BLOCK_M);
+                    for (int kb = 0; kb < g.k_blocks; kb++)
+                    {
+                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        tma_load_2d(&tmap_a, &ctl->full[stage], sa, kb * g.block_k, m0);
+                        tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
+                        if (++stage == g.stages) stage = 0, phase ^= 1;
+                    }
                 }
             }
         }
@@ -235,26 +193,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
-                mbar_wait(&ctl->tmem_empty[as], aphase ^ 1); // epilogue has drained this accumulator
+                const long long mt0 = (st / g.n_tiles) * g.mt;
+                mbar_wait(&ctl->tmem_empty[as], aphase ^ 1); // the epilogue has drained this accumulator stage
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * g.block_n);
-                for (int kb = 0; kb < g.k_blocks; kb++)
+                for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
                 {
-                    mbar_wait(&ctl->full[stage], phase); // TMA bytes have landed
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t da = make_smem_desc(sa, g.swizzle), db = make_smem_desc(sa + a_bytes, g.swizzle);
-                    for (int k = 0; k < g.block_k / 32; k++)
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * acc_cols + i * g.block_n);
+                    for (int kb = 0; kb < g.k_blocks; kb++)
                     {
-                        // advance 32 bytes (one UMMA_K of int8) inside the swizzled row: +2 in 16-byte units
-                        umma_i8(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), g.idesc, (kb | k) ? 1u : 0u);
+                        mbar_wait(&ctl->full[stage], phase); // TMA bytes have landed
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint64_t da = make_smem_desc(sa, g.swizzle), db = make_smem_desc(sa + a_bytes, g.swizzle);
+                        for (int k = 0; k < g.block_k / 32; k++)
+                        {
+                            // advance 32 bytes (one UMMA_K of int8) inside the swizzled row: +2 in 16-byte units
+                            umma_i8(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), g.idesc, (kb | k) ? 1u : 0u);
+                        }
+                        tcgen05_commit(&ctl->empty[stage]); // smem stage reusable once these MMAs have read it
+                        if (++stage == g.stages) stage = 0, phase ^= 1;
                     }
-                    tcgen05_commit(&ctl->empty[stage]); // smem stage reusable once these MMAs have read it
-                    if (++stage == g.stages) stage = 0, phase ^= 1;
                 }
-                tcgen05_commit(&ctl->tmem_full[as]); // accumulator complete
+                tcgen05_commit(&ctl->tmem_full[as]); // all m-tiles of this accumulator stage are complete
                 if (++as == 2) as = 0, aphase ^= 1;
             }
         }
@@ -262,23 +224,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     else
     {
         // ===================== epilogue (warps 2..17) =====================
-        const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
-        const int split = (warp - 2) >> 2; // 0..3: which of the quarter's four warps
-        const int et = threadIdx.x - 64;   // 0..EPI_THREADS-1
-        const int opitch = g.block_n + OUT_PAD;
-        const int vec_per_row = g.block_n >> 4;
-        const uint32_t par_s = smem_u32(epi_par), ost_s = smem_u32(ostage);
+        // TMEM lane quarter q (hardware rule: a warp may only touch lanes 32*(warp_id % 4)...) is served by the four
+        // warps {q, q+4, q+8, q+12}: they deal the (m-tile, 16-column chunk) units of the stage round-robin, stage the
+        // requantised bytes of "their" rows in smem and copy them out with coalesced 16-byte stores.  Only these 128
+        // threads synchronise with each other (named barriers); nothing here is block-wide.
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int tq = sub * 32 + lane; // 0..127 inside the quarter group
+        const int nch = g.block_n >> 4; // 16-column chunks per m-tile
+        const uint32_t par_s = par_base + (uint32_t)(q * g.block_n * 8);
+        const uint32_t ost_s = ost_base + (uint32_t)(q * g.mt * 32 * opitch);
         int as = 0;
         uint32_t aphase = 0;
         int loaded_n0 = -1;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
         {
-            const long long m0 = (tile / g.n_tiles) * BLOCK_M;
-            const int n0 = (int)(tile % g.n_tiles) * g.block_n;
+            const long long mt0 = (st / g.n_tiles) * g.mt;
+            const int n0 = (int)(st % g.n_tiles) * g.block_n;
+            const long long rem = g.m_tiles - mt0;
+            const int mtc = rem < g.mt ? (int)rem : g.mt;
             if (n0 != loaded_n0)
             {
-                // per-channel fast-path constants (m, bias) of this N tile -> smem; pad / overhanging channels get (0, 0)
-                for (int c = et; c < g.block_n; c += EPI_THREADS)
+                // per-channel fast-path constants (m, bias) of this N tile; pad / overhanging channels get (0, 0)
+                for (int c = tq; c < g.block_n; c += 128)
                 {
                     const int oc = n0 + c;
                     sts_f2(par_s + c * 8, (oc < g.ocp && e.fast_ok) ? __ldg(e.fast_par + oc) : make_float2(0.f, 0.f));
@@ -287,61 +255,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             mbar_wait(&ctl->tmem_full[as], aphase);
             tcgen05_fence_after();
-            epi_bar_sync(1); // A: constants visible; everybody finished copying the previous tile out of `ostage`
-            const int rloc = q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.block_n);
-            const uint32_t srow = ost_s + (uint32_t)(rloc * opitch);
-            for (int c = split * 16; c < g.block_n; c += 16 * (EPI_WARPS / 4))
+            quarter_bar_sync(1 + q); // A: constants visible; the group finished copying the previous stage out
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
+            const int units = mtc * nch;
+            uint32_t va[16], vb[16];
+            int u = sub;
+            if (u < units) tmem_ld16(tbase + (u / nch) * g.block_n + (u % nch) * 16, va);
+            while (u < units)
             {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
                 tmem_ld_wait();
-                uint32_t w[4];
-                if (e.fast_ok)
+                int un = u + 4;
+                if (un < units) tmem_ld16(tbase + (un / nch) * g.block_n + (un % nch) * 16, vb);
                 {
-                    uint32_t bad = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        const float4 p01 = lds_f4(par_s + (c + j * 4) * 8);
-                        const float4 p23 = lds_f4(par_s + (c + j * 4 + 2) * 8);
-                        const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
-                        const int32_t b4[4] = {__float_as_int(p01.y), __float_as_int(p01.w), __float_as_int(p23.y), __float_as_int(p23.w)};
-                        const int32_t a4[4] = {(int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3]};
-                        w[j] = requant_fast4<false>(a4, e, m4, b4, bad, 1u << (4 * j));
-                    }
-                    if (bad)
-                    {
-                        // rare (2.4e-4 of the elements): exact recomputation; fully unrolled so v[] stays in registers
-#pragma unroll
-                        for (int k = 0; k < 16; k++)
-                            if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, (int32_t)v[k], n0 + c + k, e);
-                    }
+                    const int i = u / nch, c = (u % nch) * 16;
+                    epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
                 }
-                else
+                u = un;
+                if (u >= units) break;
+                tmem_ld_wait();
+                un = u + 4;
+                if (un < units) tmem_ld16(tbase + (un / nch) * g.block_n + (un % nch) * 16, va);
                 {
-                    // degenerate scales: literal arithmetic for every element
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                    {
-                        if ((k & 3) == 0) w[k >> 2] = 0;
-                        if (n0 + c + k < g.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], n0 + c + k, e) & 0xffu) << (8 * (k & 3));
-                    }
+                    const int i = u / nch, c = (u % nch) * 16;
+                    epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
                 }
-                sts_u4(srow + c, w[0], w[1], w[2], w[3]);
+                u = un;
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]); // accumulator drained: the MMA warp may overwrite it
             if (++as == 2) as = 0, aphase ^= 1;
-            epi_bar_sync(2); // B: the staged tile is complete
-            // coalesced copy-out: consecutive threads write consecutive 16-byte pieces of a row, then the next row
-            const int total_vec = BLOCK_M * vec_per_row;
-            for (int vi = et; vi < total_vec; vi += EPI_THREADS)
+            quarter_bar_sync(5 + q); // B: the quarter's staged rows are complete
+            // coalesced copy-out of this quarter's rows: consecutive threads write consecutive 16-byte pieces
+            const int total_vec = mtc * 32 * nch;
+            for (int vi = tq; vi < total_vec; vi += 128)
             {
-                const int r = vi / vec_per_row, cv = vi - r * vec_per_row;
-                if (m0 + r < g.m && n0 + cv * 16 < g.ocp)
-                    *reinterpret_cast<uint4*>(out + (size_t)(m0 + r) * g.ldo + n0 + cv * 16) = lds_u4(ost_s + (uint32_t)(r * opitch + cv * 16));
+                const int lr = g.vshift >= 0 ? (vi >> g.vshift) : (vi / nch);
+                const int cv = vi - lr * nch;
+                const long long grow = (mt0 + (lr >> 5)) * BLOCK_M + q * 32 + (lr & 31);
+                if (grow < g.m && n0 + cv * 16 < g.ocp)
+                    *reinterpret_cast<uint4*>(out + (size_t)grow * g.ldo + n0 + cv * 16) = lds_u4(ost_s + (uint32_t)(lr * opitch + cv * 16));
             }
         }
     }
@@ -373,20 +326,30 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
-static int encode_2d(void* tmap, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner,
-                     uint32_t box_rows, int swizzle)
+int tmap_encode(void* tmap, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                const uint32_t* elem_strides, int swizzle_bytes)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return TB200_ERR_CUDA;
-    cuuint64_t dims[2] = {inner, rows};
-    cuuint64_t strides[1] = {pitch};
-    cuuint32_t box[2] = {box_inner, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                           : (swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = enc((CUtensorMap*)tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+    cuuint64_t d[5], st[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) d[i] = dims[i], bx[i] = box[i], es[i] = elem_strides ? elem_strides[i] : 1;
+    for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc((CUtensorMap*)tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TB200_ERR_CUDA;
+}
+
+static int encode_2d(void* tmap, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner,
+                     uint32_t box_rows, int swizzle)
+{
+    const uint64_t dims[2] = {inner, rows}, strides[1] = {pitch};
+    const uint32_t box[2] = {box_inner, box_rows};
+    return tmap_encode(tmap, base, 2, dims, strides, box, nullptr, swizzle);
 }
 
 int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
@@ -402,7 +365,11 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
     p->n_tiles = (ocp + p->block_n - 1) / p->block_n;
     p->m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
     const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->block_n * p->block_k + 1023) & ~1023;
-    const int epi_bytes = p->block_n * 8 + BLOCK_M * (p->block_n + OUT_PAD) + 2048;
+    // m-tiles per accumulator stage: amortise the per-stage synchronisation over ~256 TMEM columns of work
+    p->mt = 1;
+    if (p->n_tiles == 1)
+        while (p->mt < 4 && 2 * (p->mt * 2) * p->block_n <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+    const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
     int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return TB200_ERR_INVALID;
@@ -417,14 +384,22 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int
 {
     GemmArgs g;
     g.m = p.m, g.m_tiles = p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
+    g.mt = p.mt;
+    g.num_super = ((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles;
+    {
+        const int nch = p.block_n >> 4;
+        g.vshift = -1;
+        for (int sh = 0; sh < 5; sh++)
+            if ((1 << sh) == nch) g.vshift = sh;
+    }
     g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp, g.ldo = p.ldo;
     g.idesc = make_idesc_i8(p.block_n, !e.is_uint8, !e.is_uint8);
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * p.block_n)) cols <<= 1;
+    while (cols < (uint32_t)(2 * p.mt * p.block_n)) cols <<= 1;
     g.tmem_cols = cols;
     const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.block_n * p.block_k + 1023) & ~1023;
-    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + sizeof(GemmSmemCtl) + 16 + (size_t)p.block_n * 8 +
-                        (size_t)BLOCK_M * (p.block_n + OUT_PAD) + 1024;
+    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + sizeof(GemmSmemCtl) + 4 * (size_t)p.block_n * 8 +
+                        (size_t)BLOCK_M * p.mt * (p.block_n + OUT_PAD) + 1024;
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -432,8 +407,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
-    long long tiles = p.m_tiles * p.n_tiles;
-    const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+    const int grid = (int)(g.num_super < num_sms ? g.num_super : num_sms);
     CUtensorMap ta, tb;
     memcpy(&ta, p.tmap_a, sizeof ta);
     memcpy(&tb, p.tmap_b, sizeof tb);

@@ -44,6 +44,16 @@ cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int 
 cudaError_t launch_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
 cudaError_t launch_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
 
+// ---- TMA-staged depthwise 3x3 (dw_tma.cu) ---------------------------------------------------------------
+struct DwPlan
+{
+    alignas(64) unsigned char tmap_in[128]; // CUtensorMap over the NHWC input (C, W, H, N)
+    int valid;
+    int tw, gpr, rows_per_cta, tile_cols, tile_rows, smem_bytes;
+};
+int dw_plan_create(DwPlan* plan, const void* in, const ConvShape& s, const EpiParams& e);
+cudaError_t launch_conv_dw_tma(const DwPlan& plan, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+
 // ---- tcgen05 GEMM (gemm_tcgen05.cu) ------------------------------------------------------------------
 // out[M][ldo] (bytes) = requant( A[M][K] (row pitch lda bytes) . B[OCp][K]^T )
 struct GemmPlan
@@ -55,6 +65,7 @@ struct GemmPlan
     int oc, ocp; // logical / padded output channels
     int ldo;     // output row pitch in bytes
     int block_n, block_k, stages, k_blocks, n_tiles;
+    int mt; // m-tiles per accumulator stage
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
     int variant; // debug: descriptor variant selector (0 = default)

@@ -17,7 +17,7 @@ namespace tb200 {
 // ------------------------------------------------------------------------------------------------------
 template <bool U8, int OCT>
 __global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
-                                                          uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+                                                          uint8_t* __restrict__ out, const ConvShape s, const __grid_constant__ EpiParams e)
 {
     const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long)s.n * s.oh * s.ow;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restr
 // ------------------------------------------------------------------------------------------------------
 template <bool U8>
 __global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
-                                                      uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+                                                      uint8_t* __restrict__ out, const ConvShape s, const __grid_constant__ EpiParams e)
 {
     const int cw = s.cp / 4; // channel words per pixel
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------------------
 template <int TW, int S>
 __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
-                                                            uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+                                                            uint8_t* __restrict__ out, const ConvShape s, const __grid_constant__ EpiParams e)
 {
     const int cw = s.cp / 4;
     const int gpr = (s.ow + TW - 1) / TW; // pixel groups per output row
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
     uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
     if (!e.fast_ok)
     {
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < TW; t++)
             if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
         return;
@@ -249,13 +249,23 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
 // Fuses the NCHW->NHWC conversion of the graph input into the first convolution.
 // ------------------------------------------------------------------------------------------------------
 template <bool U8, int OCT>
-__global__ void __launch_bounds__(128) conv_stem_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
-                                                        uint8_t* __restrict__ out, ConvShape s, EpiParams e)
+__global__ void __launch_bounds__(128, (OCT == 32 && !U8) ? 4 : 2)
+    conv_stem_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out, const ConvShape s,
+                     const __grid_constant__ EpiParams e)
 {
+    // weights of this CTA's OCT output channels, transposed to [tap][oc] so that one LDS.128 feeds four dp4a
+    extern __shared__ __align__(16) int stem_w[];
+    const int oc0 = blockIdx.y * OCT;
+    const int taps_total = s.kh * s.kw;
+    for (int i = threadIdx.x; i < taps_total * OCT; i += blockDim.x)
+    {
+        const int t = i / OCT, j = i - t * OCT;
+        stem_w[i] = __ldg(reinterpret_cast<const int*>(wgt) + (size_t)(oc0 + j) * taps_total + t);
+    }
+    __syncthreads();
     const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long)s.n * s.oh * s.ow;
     if (pix >= npix) return;
-    const int oc0 = blockIdx.y * OCT;
     const int ow = (int)(pix % s.ow);
     const int oh = (int)((pix / s.ow) % s.oh);
     const int n = (int)(pix / ((long long)s.ow * s.oh));
@@ -263,35 +273,50 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const uint8_t* __restric
     const uint8_t* img = in + (size_t)n * s.c * plane;
 
     int acc[OCT];
-    int sw_sum[OCT];
+    int sw_sum[U8 ? OCT : 1];
 #pragma unroll
-    for (int j = 0; j < OCT; j++) acc[j] = 0, sw_sum[j] = 0;
+    for (int j = 0; j < OCT; j++) acc[j] = 0;
+    if (U8)
+    {
+#pragma unroll
+        for (int j = 0; j < (U8 ? OCT : 1); j++) sw_sum[j] = 0;
+    }
     int sx_sum = 0, taps = 0;
 
+#pragma unroll 1
     for (int kh = 0; kh < s.kh; kh++)
     {
         const int iy = oh * s.sh - s.ph0 + kh * s.dh;
         if (iy < 0 || iy >= s.h) continue;
+#pragma unroll 1
         for (int kw = 0; kw < s.kw; kw++)
         {
             const int ix = ow * s.sw - s.pw0 + kw * s.dw;
             if (ix < 0 || ix >= s.w) continue;
             taps++;
-            unsigned xv = 0;
-            for (int c = 0; c < s.c; c++) xv |= (unsigned)__ldg(img + c * plane + (size_t)iy * s.w + ix) << (8 * c);
+            const uint8_t* px = img + (size_t)iy * s.w + ix;
+            unsigned xv = __ldg(px);
+            if (s.c > 1) xv |= (unsigned)__ldg(px + plane) << 8;
+            if (s.c > 2) xv |= (unsigned)__ldg(px + 2 * plane) << 16;
+            if (s.c > 3) xv |= (unsigned)__ldg(px + 3 * plane) << 24;
             if (U8) sx_sum = (int)dp4a_u8(xv, 0x01010101u, (unsigned)sx_sum);
-            const int* wp = reinterpret_cast<const int*>(wgt) + ((size_t)oc0 * s.kh + kh) * s.kw + kw;
+            const int4* wrow = reinterpret_cast<const int4*>(stem_w + (kh * s.kw + kw) * OCT);
 #pragma unroll
-            for (int j = 0; j < OCT; j++)
+            for (int j = 0; j < OCT; j += 4)
             {
-                const int wv = __ldg(wp + (size_t)j * s.kh * s.kw);
-                if (U8)
+                const int4 wv = wrow[j >> 2];
+                const int w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++)
                 {
-                    acc[j] = (int)dp4a_u8(xv, (unsigned)wv, (unsigned)acc[j]);
-                    sw_sum[j] = (int)dp4a_u8((unsigned)wv, 0x01010101u, (unsigned)sw_sum[j]);
+                    if (U8)
+                    {
+                        acc[j + t] = (int)dp4a_u8(xv, (unsigned)w4[t], (unsigned)acc[j + t]);
+                        sw_sum[j + t] = (int)dp4a_u8((unsigned)w4[t], 0x01010101u, (unsigned)sw_sum[j + t]);
+                    }
+                    else
+                        acc[j + t] = dp4a_s8((int)xv, w4[t], acc[j + t]);
                 }
-                else
-                    acc[j] = dp4a_s8((int)xv, wv, acc[j]);
             }
         }
     }
@@ -600,13 +625,15 @@ cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const Con
     if (s.ocp % 32 == 0)
     {
         dim3 grid(blocks_for(npix, 128), s.ocp / 32);
-        if (e.is_uint8) conv_stem_kernel<true, 32><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
-        else conv_stem_kernel<false, 32><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        const size_t sm = (size_t)s.kh * s.kw * 32 * 4;
+        if (e.is_uint8) conv_stem_kernel<true, 32><<<grid, 128, sm, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+        else conv_stem_kernel<false, 32><<<grid, 128, sm, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
         return cudaGetLastError();
     }
     dim3 grid(blocks_for(npix, 128), s.ocp / 16);
-    if (e.is_uint8) conv_stem_kernel<true, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
-    else conv_stem_kernel<false, 16><<<grid, 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    const size_t sm16 = (size_t)s.kh * s.kw * 16 * 4;
+    if (e.is_uint8) conv_stem_kernel<true, 16><<<grid, 128, sm16, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
+    else conv_stem_kernel<false, 16><<<grid, 128, sm16, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     return cudaGetLastError();
 }
 
