@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -51,6 +52,7 @@ enum StepKind
     K_CONV_DW,
     K_CONV_DIRECT,
     K_GEMM,
+    K_IGEMM,
     K_POOL,
     K_POINTWISE,
     K_CONCAT_PART,
@@ -58,7 +60,7 @@ enum StepKind
     K_COPY
 };
 static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_dw_direct", "conv_direct_dp4a",
-                                  "gemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy"};
+                                  "gemm_i8_tcgen05", "conv_igemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy"};
 
 struct Step
 {
@@ -109,8 +111,13 @@ struct tb200_graph
     size_t act_bytes = 0;
     uint8_t* w_arena = nullptr;
     size_t w_bytes = 0;
-    cudaGraph_t cu_graph = nullptr;
-    cudaGraphExec_t cu_exec = nullptr;
+    int chunks = 1;
+    std::vector<std::vector<Step>> chunk_steps;
+    std::vector<cudaGraph_t> cu_graphs;
+    std::vector<cudaGraphExec_t> cu_execs;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out;
+    cudaEvent_t ev_done = nullptr;
     double work_ops = 0, work_bytes = 0;
     int num_launches = 0;
 };
@@ -254,7 +261,8 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
         err = s.dwp.valid ? launch_conv_dw_tma(s.dwp, s.w, s.out, s.cs, s.epi, st) : launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st);
         break;
     case K_CONV_DIRECT: err = launch_conv_direct(s.in, s.w, s.out, s.cs, s.epi, st); break;
-    case K_GEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, g->ctx->num_sms, st); break;
+    case K_GEMM:
+    case K_IGEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, g->ctx->num_sms, st); break;
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
     case K_POINTWISE: err = launch_pointwise(s.in, s.in2, s.out, s.bytes, s.pp, s.u8, st); break;
     case K_CONCAT_PART:
@@ -271,8 +279,13 @@ static void destroy_graph(tb200_graph* g)
 {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
-    if (g->cu_exec) cudaGraphExecDestroy(g->cu_exec);
-    if (g->cu_graph) cudaGraphDestroy(g->cu_graph);
+    for (auto e : g->cu_execs) if (e) cudaGraphExecDestroy(e);
+    for (auto c : g->cu_graphs) if (c) cudaGraphDestroy(c);
+    for (auto e : g->ev_in) cudaEventDestroy(e);
+    for (auto e : g->ev_out) cudaEventDestroy(e);
+    if (g->ev_done) cudaEventDestroy(g->ev_done);
+    if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+    if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
     for (auto p : g->in_nchw_dev) cudaFree(p);
     for (auto p : g->out_nchw_dev) cudaFree(p);
     cudaFree(g->act_arena);
@@ -357,6 +370,10 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             else if (!no_tc && !u8 && L.group == 1 && L.kernel_h == 1 && L.kernel_w == 1 && L.stride_h == 1 && L.stride_w == 1 &&
                      !L.pad_h0 && !L.pad_h1 && !L.pad_w0 && !L.pad_w1)
                 kind[li] = K_GEMM, wsize = (size_t)tout.cp * tin.cp;
+            else if (!no_tc && !u8 && L.group == 1 && L.dilation_h == 1 && L.dilation_w == 1 && L.stride_h == L.stride_w &&
+                     (L.stride_h == 1 || L.stride_h == 2) && (L.kernel_h * L.kernel_w == 1 || tin.cp % 32 == 0) && tout.d.dims[3] <= 4096 &&
+                     !getenv("TB200_NO_IGEMM"))
+                kind[li] = K_IGEMM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * tin.cp; // same packing as the direct kernel
             else
             {
                 if (L.group > 1 && ((cg % 4) || ((OC / L.group) % 4)))
@@ -501,144 +518,187 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
 
-    // ---- build the launch sequence ----
-    for (size_t i = 0; i < g->input_ids.size(); i++)
+    // ---- build the launch sequence: the batch is cut into K equal chunks (images are independent units) so that `run`
+    //      can overlap the H2D copy of chunk i+1 with the kernels of chunk i; each chunk owns a slice of every tensor ----
+    int Ntot = g->tensors[0].d.dims[0];
+    bool same_batch = true;
+    for (auto& t : g->tensors) same_batch &= (t.d.dims[0] == Ntot);
+    int K = 1;
+    if (same_batch && !(flags & TB200_PRERUN_NO_GRAPH))
     {
-        TensorInfo& t = g->tensors[g->input_ids[i]];
-        if (!t.nhwc_needed) continue;
-        Step s;
-        s.kind = K_NCHW2NHWC, s.layer = -1, s.in = g->in_nchw_dev[i], s.out = t.dev;
-        s.n = t.d.dims[0], s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
-        g->steps.push_back(s);
+        K = Ntot >= 64 ? 4 : (Ntot >= 16 ? 2 : 1);
+        if (const char* ev = getenv("TB200_PIPELINE_CHUNKS")) K = atoi(ev) > 0 ? atoi(ev) : K;
+        while (K > 1 && Ntot % K) K--;
     }
-    for (int li = 0; li < num_layers; li++)
+    g->chunks = K;
+    g->chunk_steps.resize(K);
+    const int nb = Ntot / K;
+    for (int ck = 0; ck < K; ck++)
     {
-        const tb200_layer_desc& L = layers[li];
-        TensorInfo& tin = g->tensors[L.inputs[0]];
-        TensorInfo& tout = g->tensors[L.output];
-        const bool u8 = tin.d.data_type == TB200_DT_UINT8;
-        Step s;
-        s.kind = kind[li], s.layer = li, s.u8 = u8;
-        s.in = tin.dev, s.out = tout.dev;
-        const int N = tin.d.dims[0], C = tin.d.dims[1], H = tin.d.dims[2], W = tin.d.dims[3];
-        const int OC = tout.d.dims[1], OH = tout.d.dims[2], OW = tout.d.dims[3];
-        if (L.op == TB200_OP_CONV || L.op == TB200_OP_FC)
+        std::vector<Step>& steps = g->chunk_steps[ck];
+        auto tdev = [&](const TensorInfo& t) -> uint8_t* { return t.dev + (size_t)ck * (t.nhwc_bytes / K); };
+        for (size_t i = 0; i < g->input_ids.size(); i++)
         {
-            const bool fc = L.op == TB200_OP_FC;
-            s.w = g->w_arena + blobs[li].w_off;
-            s.epi = make_epi(L, tin.d, tout.d, fc);
-            s.epi.bias = (const int32_t*)(g->w_arena + blobs[li].bias_off);
-            s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
-            s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
-            ConvShape& cs = s.cs;
-            cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
-            if (fc)
+            TensorInfo& t = g->tensors[g->input_ids[i]];
+            if (!t.nhwc_needed) continue;
+            Step s;
+            s.kind = K_NCHW2NHWC, s.layer = -1, s.in = g->in_nchw_dev[i] + ck * (t.nchw_bytes / K), s.out = tdev(t);
+            s.n = nb, s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
+            steps.push_back(s);
+        }
+        for (int li = 0; li < num_layers; li++)
+        {
+            const tb200_layer_desc& L = layers[li];
+            TensorInfo& tin = g->tensors[L.inputs[0]];
+            TensorInfo& tout = g->tensors[L.output];
+            const bool u8 = tin.d.data_type == TB200_DT_UINT8;
+            Step s;
+            s.kind = kind[li], s.layer = li, s.u8 = u8;
+            s.in = tdev(tin), s.out = tdev(tout);
+            const int N = nb, C = tin.d.dims[1], H = tin.d.dims[2], W = tin.d.dims[3];
+            const int OC = tout.d.dims[1], OH = tout.d.dims[2], OW = tout.d.dims[3];
+            if (L.op == TB200_OP_CONV || L.op == TB200_OP_FC)
             {
-                cs.kh = H, cs.kw = W, cs.sh = cs.sw = 1, cs.ph0 = cs.pw0 = 0, cs.dh = cs.dw = 1, cs.group = 1;
-                cs.cg = C, cs.cgp = tin.cp;
-                g->work_ops += 2.0 * N * OC * C * H * W;
-                g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * C * H * W + (L.bias ? 4.0 * OC : 0);
+                const bool fc = L.op == TB200_OP_FC;
+                s.w = g->w_arena + blobs[li].w_off;
+                s.epi = make_epi(L, tin.d, tout.d, fc);
+                s.epi.bias = (const int32_t*)(g->w_arena + blobs[li].bias_off);
+                s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
+                s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
+                ConvShape& cs = s.cs;
+                cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
+                if (fc)
+                {
+                    cs.kh = H, cs.kw = W, cs.sh = cs.sw = 1, cs.ph0 = cs.pw0 = 0, cs.dh = cs.dw = 1, cs.group = 1;
+                    cs.cg = C, cs.cgp = tin.cp;
+                    if (ck == 0)
+                    {
+                        g->work_ops += 2.0 * Ntot * OC * C * H * W;
+                        g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * C * H * W + (L.bias ? 4.0 * OC : 0);
+                    }
+                }
+                else
+                {
+                    cs.kh = L.kernel_h, cs.kw = L.kernel_w, cs.sh = L.stride_h, cs.sw = L.stride_w, cs.ph0 = L.pad_h0, cs.pw0 = L.pad_w0;
+                    cs.dh = L.dilation_h, cs.dw = L.dilation_w, cs.group = L.group;
+                    cs.cg = C / L.group, cs.cgp = (L.group == 1) ? tin.cp : cs.cg;
+                    const double k = (double)cs.cg * cs.kh * cs.kw;
+                    if (ck == 0)
+                    {
+                        g->work_ops += 2.0 * (double)tout.nchw_bytes * k;
+                        g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
+                    }
+                }
+                if (s.kind == K_CONV_STEM) s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
+                if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
+                if (s.kind == K_GEMM)
+                {
+                    const long long m = fc ? N : (long long)N * H * W;
+                    const int kdim = fc ? H * W * tin.cp : tin.cp;
+                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, m, kdim, OC, tout.cp, tout.cp, 0);
+                    if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
+                }
             }
-            else
+            else if (L.op == TB200_OP_POOL)
             {
-                cs.kh = L.kernel_h, cs.kw = L.kernel_w, cs.sh = L.stride_h, cs.sw = L.stride_w, cs.ph0 = L.pad_h0, cs.pw0 = L.pad_w0;
-                cs.dh = L.dilation_h, cs.dw = L.dilation_w, cs.group = L.group;
-                cs.cg = C / L.group, cs.cgp = (L.group == 1) ? tin.cp : cs.cg;
-                const double k = (double)cs.cg * cs.kh * cs.kw;
-                g->work_ops += 2.0 * (double)tout.nchw_bytes * k;
-                g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
+                PoolShape& p = s.ps;
+                p.n = N, p.h = H, p.w = W, p.c = C, p.cp = tin.cp, p.oh = OH, p.ow = OW;
+                p.kh = L.kernel_h, p.kw = L.kernel_w, p.sh = L.stride_h, p.sw = L.stride_w, p.ph0 = L.pad_h0, p.pw0 = L.pad_w0;
+                p.method = L.pool_method, p.caffe_flavor = L.caffe_flavor;
+                p.in_scale = tin.d.scale, p.out_scale = tout.d.scale, p.in_zero = tin.d.zero_point, p.out_zero = tout.d.zero_point;
+                if (L.pool_global) p.kh = H, p.kw = W, p.sh = p.sw = 1, p.ph0 = p.pw0 = 0;
+                if (tout.d.dims[1] != C) return bail(fail(TB200_ERR_INVALID, "layer %d: pool channel mismatch", li));
             }
-            if (s.kind == K_CONV_STEM) s.in = g->in_nchw_dev[tin.input_index];
-            if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
-            if (s.kind == K_GEMM)
+            else if (L.op == TB200_OP_RELU || L.op == TB200_OP_ELTWISE)
             {
-                const long long m = fc ? N : (long long)N * H * W;
-                const int kdim = fc ? H * W * tin.cp : tin.cp;
-                int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, m, kdim, OC, tout.cp, tout.cp, 0);
-                if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
+                PointwiseParams& p = s.pp;
+                p.c = C, p.cp = tin.cp;
+                p.scale0 = tin.d.scale, p.zero0 = tin.d.zero_point, p.out_scale = tout.d.scale, p.out_zero = tout.d.zero_point;
+                p.negative_slope = L.negative_slope;
+                if (L.op == TB200_OP_RELU)
+                    p.mode = 0, p.scale1 = 0, p.zero1 = 0;
+                else
+                {
+                    const TensorInfo& t1 = g->tensors[L.inputs[1]];
+                    if (t1.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: eltwise broadcast", li));
+                    p.mode = L.elt_type == TB200_ELT_SUM ? 1 : 2;
+                    p.scale1 = t1.d.scale, p.zero1 = t1.d.zero_point;
+                    s.in2 = tdev(t1);
+                }
+                s.bytes = (long long)(tin.nhwc_bytes / K);
+                if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: pointwise shape mismatch", li));
             }
-        }
-        else if (L.op == TB200_OP_POOL)
-        {
-            PoolShape& p = s.ps;
-            p.n = N, p.h = H, p.w = W, p.c = C, p.cp = tin.cp, p.oh = OH, p.ow = OW;
-            p.kh = L.kernel_h, p.kw = L.kernel_w, p.sh = L.stride_h, p.sw = L.stride_w, p.ph0 = L.pad_h0, p.pw0 = L.pad_w0;
-            p.method = L.pool_method, p.caffe_flavor = L.caffe_flavor;
-            p.in_scale = tin.d.scale, p.out_scale = tout.d.scale, p.in_zero = tin.d.zero_point, p.out_zero = tout.d.zero_point;
-            if (L.pool_global) p.kh = H, p.kw = W, p.sh = p.sw = 1, p.ph0 = p.pw0 = 0;
-            if (tout.d.dims[1] != C) return bail(fail(TB200_ERR_INVALID, "layer %d: pool channel mismatch", li));
-        }
-        else if (L.op == TB200_OP_RELU || L.op == TB200_OP_ELTWISE)
-        {
-            PointwiseParams& p = s.pp;
-            p.c = C, p.cp = tin.cp;
-            p.scale0 = tin.d.scale, p.zero0 = tin.d.zero_point, p.out_scale = tout.d.scale, p.out_zero = tout.d.zero_point;
-            p.negative_slope = L.negative_slope;
-            if (L.op == TB200_OP_RELU)
-                p.mode = 0, p.scale1 = 0, p.zero1 = 0;
-            else
+            else if (L.op == TB200_OP_CONCAT && L.num_inputs > 1)
             {
-                const TensorInfo& t1 = g->tensors[L.inputs[1]];
-                if (t1.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: eltwise broadcast", li));
-                p.mode = L.elt_type == TB200_ELT_SUM ? 1 : 2;
-                p.scale1 = t1.d.scale, p.zero1 = t1.d.zero_point;
-                s.in2 = t1.dev;
+                int coff = 0;
+                for (int k = 0; k < L.num_inputs; k++)
+                {
+                    const TensorInfo& tk = g->tensors[L.inputs[k]];
+                    Step p = s;
+                    p.in = tdev(tk);
+                    p.npix = (long long)N * H * W, p.c = tk.d.dims[1], p.cp_in = tk.cp, p.cp_out = tout.cp, p.c_off = coff;
+                    p.s_in = tk.d.scale, p.z_in = tk.d.zero_point, p.s_out = tout.d.scale, p.z_out = tout.d.zero_point;
+                    coff += tk.d.dims[1];
+                    if (k + 1 < L.num_inputs) steps.push_back(p);
+                    else s = p;
+                }
+                if (coff != OC) return bail(fail(TB200_ERR_INVALID, "layer %d: concat channels %d != %d", li, coff, OC));
             }
-            s.bytes = (long long)tin.nhwc_bytes;
-            if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: pointwise shape mismatch", li));
-        }
-        else if (L.op == TB200_OP_CONCAT && L.num_inputs > 1)
-        {
-            int coff = 0;
-            for (int k = 0; k < L.num_inputs; k++)
+            else if (L.op == TB200_OP_UPSAMPLE)
             {
-                const TensorInfo& tk = g->tensors[L.inputs[k]];
-                Step p = s;
-                p.in = tk.dev;
-                p.npix = (long long)N * H * W, p.c = tk.d.dims[1], p.cp_in = tk.cp, p.cp_out = tout.cp, p.c_off = coff;
-                p.s_in = tk.d.scale, p.z_in = tk.d.zero_point, p.s_out = tout.d.scale, p.z_out = tout.d.zero_point;
-                coff += tk.d.dims[1];
-                if (k + 1 < L.num_inputs) g->steps.push_back(p);
-                else s = p;
+                s.n = N, s.h = H, s.w_ = W, s.cp_in = tin.cp, s.scale = L.up_scale;
+                if (OH != H * L.up_scale || OW != W * L.up_scale) return bail(fail(TB200_ERR_INVALID, "layer %d: upsample shape", li));
             }
-            if (coff != OC) return bail(fail(TB200_ERR_INVALID, "layer %d: concat channels %d != %d", li, coff, OC));
+            else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT)
+            {
+                s.bytes = (long long)(tin.nhwc_bytes / K);
+                if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));
+            }
+            g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : kStepName[s.kind];
+            steps.push_back(s);
         }
-        else if (L.op == TB200_OP_UPSAMPLE)
+        for (size_t i = 0; i < g->output_ids.size(); i++)
         {
-            s.n = N, s.h = H, s.w_ = W, s.cp_in = tin.cp, s.scale = L.up_scale;
-            if (OH != H * L.up_scale || OW != W * L.up_scale) return bail(fail(TB200_ERR_INVALID, "layer %d: upsample shape", li));
+            TensorInfo& t = g->tensors[g->output_ids[i]];
+            Step s;
+            s.kind = K_NHWC2NCHW, s.layer = -1, s.in = tdev(t), s.out = g->out_nchw_dev[i] + ck * (t.nchw_bytes / K);
+            s.n = nb, s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
+            steps.push_back(s);
         }
-        else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT)
-        {
-            s.bytes = (long long)tin.nhwc_bytes;
-            if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));
-        }
-        g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : kStepName[s.kind];
-        g->steps.push_back(s);
     }
-    for (size_t i = 0; i < g->output_ids.size(); i++)
-    {
-        TensorInfo& t = g->tensors[g->output_ids[i]];
-        Step s;
-        s.kind = K_NHWC2NCHW, s.layer = -1, s.in = t.dev, s.out = g->out_nchw_dev[i];
-        s.n = t.d.dims[0], s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
-        g->steps.push_back(s);
-    }
+    for (auto& cs : g->chunk_steps) g->steps.insert(g->steps.end(), cs.begin(), cs.end());
     g->num_launches = (int)g->steps.size();
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 
-    // ---- capture into a CUDA graph ----
+    // ---- capture each chunk's launch sequence into a CUDA graph ----
     if (!(flags & TB200_PRERUN_NO_GRAPH))
     {
-        CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = 0;
-        for (const Step& s : g->steps)
-            if ((rc = run_step(g, s, ctx->stream)) != 0) break;
-        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g->cu_graph);
-        if (rc) return bail(rc);
-        if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)));
-        ce = cudaGraphInstantiate(&g->cu_exec, g->cu_graph, 0);
-        if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)));
+        g->cu_graphs.assign(K, nullptr);
+        g->cu_execs.assign(K, nullptr);
+        for (int ck = 0; ck < K; ck++)
+        {
+            CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = 0;
+            for (const Step& s : g->chunk_steps[ck])
+                if ((rc = run_step(g, s, ctx->stream)) != 0) break;
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g->cu_graphs[ck]);
+            if (rc) return bail(rc);
+            if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)));
+            ce = cudaGraphInstantiate(&g->cu_execs[ck], g->cu_graphs[ck], 0);
+            if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)));
+        }
+        if (K > 1)
+        {
+            CUDA_OK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&g->d2h_stream, cudaStreamNonBlocking));
+            g->ev_in.resize(K), g->ev_out.resize(K);
+            for (int ck = 0; ck < K; ck++)
+            {
+                CUDA_OK(cudaEventCreateWithFlags(&g->ev_in[ck], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&g->ev_out[ck], cudaEventDisableTiming));
+            }
+            CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+        }
     }
     *out = g;
     return 0;
@@ -659,9 +719,9 @@ int tb200_graph_launch(tb200_graph* g)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
     CUDA_OK(cudaSetDevice(g->ctx->device));
-    if (g->cu_exec)
+    if (!g->cu_execs.empty())
     {
-        CUDA_OK(cudaGraphLaunch(g->cu_exec, g->ctx->stream));
+        for (auto e : g->cu_execs) CUDA_OK(cudaGraphLaunch(e, g->ctx->stream));
         return 0;
     }
     for (const Step& s : g->steps)
@@ -692,12 +752,48 @@ int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const*
 {
     if (!g || !host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "bad run arguments");
     int rc;
-    for (size_t i = 0; i < g->input_ids.size(); i++)
-        if ((rc = tb200_graph_upload(g, (int)i, host_inputs[i])) != 0) return rc;
-    if ((rc = tb200_graph_launch(g)) != 0) return rc;
-    for (size_t i = 0; i < g->output_ids.size(); i++)
-        if ((rc = tb200_graph_download(g, (int)i, host_outputs[i])) != 0) return rc;
-    return tb200_graph_sync(g);
+    if (g->chunks <= 1 || g->cu_execs.empty())
+    {
+        for (size_t i = 0; i < g->input_ids.size(); i++)
+            if ((rc = tb200_graph_upload(g, (int)i, host_inputs[i])) != 0) return rc;
+        if ((rc = tb200_graph_launch(g)) != 0) return rc;
+        for (size_t i = 0; i < g->output_ids.size(); i++)
+            if ((rc = tb200_graph_download(g, (int)i, host_outputs[i])) != 0) return rc;
+        return tb200_graph_sync(g);
+    }
+    // Pipelined: the H2D copies of all chunks are queued back to back on the copy stream (the link stays busy), chunk k's
+    // kernels start as soon as ITS slice has landed, and its outputs leave on a third stream while chunk k+1 computes.
+    CUDA_OK(cudaSetDevice(g->ctx->device));
+    const int K = g->chunks;
+    cudaStream_t cs = g->ctx->stream;
+    CUDA_OK(cudaEventRecord(g->ev_done, cs)); // order after whatever the caller queued on the context stream
+    CUDA_OK(cudaStreamWaitEvent(g->copy_stream, g->ev_done, 0));
+    for (int ck = 0; ck < K; ck++)
+    {
+        for (size_t i = 0; i < g->input_ids.size(); i++)
+        {
+            const size_t bytes = g->tensors[g->input_ids[i]].nchw_bytes / K;
+            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i] + ck * bytes, (const uint8_t*)host_inputs[i] + ck * bytes, bytes, cudaMemcpyHostToDevice,
+                                    g->copy_stream));
+        }
+        CUDA_OK(cudaEventRecord(g->ev_in[ck], g->copy_stream));
+    }
+    for (int ck = 0; ck < K; ck++)
+    {
+        CUDA_OK(cudaStreamWaitEvent(cs, g->ev_in[ck], 0));
+        CUDA_OK(cudaGraphLaunch(g->cu_execs[ck], cs));
+        CUDA_OK(cudaEventRecord(g->ev_out[ck], cs));
+        CUDA_OK(cudaStreamWaitEvent(g->d2h_stream, g->ev_out[ck], 0));
+        for (size_t i = 0; i < g->output_ids.size(); i++)
+        {
+            const size_t bytes = g->tensors[g->output_ids[i]].nchw_bytes / K;
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + ck * bytes, g->out_nchw_dev[i] + ck * bytes, bytes, cudaMemcpyDeviceToHost,
+                                    g->d2h_stream));
+        }
+    }
+    CUDA_OK(cudaStreamSynchronize(g->d2h_stream));
+    CUDA_OK(cudaStreamSynchronize(cs));
+    return 0;
 }
 
 int tb200_graph_postrun(tb200_graph* g)

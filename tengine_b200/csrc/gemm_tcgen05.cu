@@ -60,14 +60,45 @@ __host__ __device__ inline uint32_t make_idesc_i8(int block_n, bool a_signed, bo
 
 struct GemmArgs
 {
-    long long m, m_tiles, num_super;
+    long long m;
+    int m_tiles, num_super; // 32-bit on purpose: 64-bit divisions in the tile decode cost ~100 instructions each
     int k_blocks, n_tiles, block_n, block_k, stages, swizzle;
     int mt;     // m-tiles (128 rows each) per accumulator stage
-    int vshift; // log2(block_n / 16) when that is a power of two, else -1
+    uint32_t nch_rcp, bw_rcp, bh_rcp; // ceil(65536/d): q = (x * rcp) >> 16 is exact for x < 4096, d <= 256
     int oc, ocp, ldo;
     uint32_t idesc;
     uint32_t tmem_cols;
+    // conv mode (implicit GEMM): an m-tile is a bw x bh x bn patch of output pixels, a k-block is (tap, channel block)
+    int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp;
+    int bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
+    uint32_t a_tx_bytes; // bytes one A load delivers (block_k * rows of the patch)
 };
+
+// m-tile -> first output pixel coordinates (conv mode)
+__device__ __forceinline__ void tile_origin(const GemmArgs& g, int mt, int& n0, int& oh0, int& ow0)
+{
+    const int r = mt / g.tiles_w;
+    ow0 = (mt - r * g.tiles_w) * g.bw;
+    const int nn = r / g.tiles_h;
+    oh0 = (r - nn * g.tiles_h) * g.bh;
+    n0 = nn * g.bn;
+}
+
+// row r of m-tile mt -> linear output pixel index, or -1 when the row is padding of the tile
+__device__ __forceinline__ long long row_pixel(const GemmArgs& g, int mt, int r)
+{
+    if (!g.conv)
+    {
+        const long long px = (long long)mt * BLOCK_M + r;
+        return px < g.m ? px : -1;
+    }
+    int n0, oh0, ow0;
+    tile_origin(g, mt, n0, oh0, ow0);
+    const int t = (int)(((uint32_t)r * g.bw_rcp) >> 16), w = r - t * g.bw;
+    const int n = (int)(((uint32_t)t * g.bh_rcp) >> 16), h = t - n * g.bh;
+    if (n >= g.bn || n0 + n >= g.nimg || oh0 + h >= g.oh || ow0 + w >= g.ow) return -1;
+    return ((long long)(n0 + n) * g.oh + oh0 + h) * g.ow + ow0 + w;
+}
 
 struct __align__(16) GemmSmemCtl
 {
@@ -164,20 +195,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
+            for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
-                const long long mt0 = (st / g.n_tiles) * g.mt;
-                const int n0 = (int)(st % g.n_tiles) * g.block_n;
+                const int msup = st / g.n_tiles;
+                const int mt0 = msup * g.mt;
+                const int n0 = (st - msup * g.n_tiles) * g.block_n;
                 for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
                 {
-                    const int m0 = (int)((mt0 + i) * BLOCK_M);
+                    const int m0 = (mt0 + i) * BLOCK_M;
+                    int cn0 = 0, coh0 = 0, cow0 = 0;
+                    if (g.conv) tile_origin(g, mt0 + i, cn0, coh0, cow0);
                     for (int kb = 0; kb < g.k_blocks; kb++)
                     {
                         mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        tma_load_2d(&tmap_a, &ctl->full[stage], sa, kb * g.block_k, m0);
-                        tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
+                        if (!g.conv)
+                        {
+                            mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+                            tma_load_2d(&tmap_a, &ctl->full[stage], sa, kb * g.block_k, m0);
+                            tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
+                        }
+                        else
+                        {
+                            // k-block = (filter tap, channel block): the A tile is the output patch shifted by the tap;
+                            // coordinates outside the image are zero-filled by the TMA unit = the convolution's padding
+                            const int tap = kb / g.cblocks, cb = kb - tap * g.cblocks;
+                            const int kh = tap / g.kw_n, kw = tap - kh * g.kw_n;
+                            mbar_expect_tx(&ctl->full[stage], g.a_tx_bytes + b_bytes);
+                            tma_load_4d(&tmap_a, &ctl->full[stage], sa, cb * g.block_k, cow0 * g.cstride - g.pad_w + kw,
+                                        coh0 * g.cstride - g.pad_h + kh, cn0);
+                            tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, tap * g.cp + cb * g.block_k, n0);
+                        }
                         if (++stage == g.stages) stage = 0, phase ^= 1;
                     }
                 }
@@ -193,9 +241,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
+            for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
-                const long long mt0 = (st / g.n_tiles) * g.mt;
+                const int mt0 = (st / g.n_tiles) * g.mt;
                 mbar_wait(&ctl->tmem_empty[as], aphase ^ 1); // the epilogue has drained this accumulator stage
                 tcgen05_fence_after();
                 for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
@@ -237,12 +285,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         int as = 0;
         uint32_t aphase = 0;
         int loaded_n0 = -1;
-        for (long long st = blockIdx.x; st < g.num_super; st += gridDim.x)
+        for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
         {
-            const long long mt0 = (st / g.n_tiles) * g.mt;
-            const int n0 = (int)(st % g.n_tiles) * g.block_n;
-            const long long rem = g.m_tiles - mt0;
-            const int mtc = rem < g.mt ? (int)rem : g.mt;
+            const int msup = st / g.n_tiles;
+            const int mt0 = msup * g.mt;
+            const int n0 = (st - msup * g.n_tiles) * g.block_n;
+            const int rem = g.m_tiles - mt0;
+            const int mtc = rem < g.mt ? rem : g.mt;
             if (n0 != loaded_n0)
             {
                 // per-channel fast-path constants (m, bias) of this N tile; pad / overhanging channels get (0, 0)
@@ -260,23 +309,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int units = mtc * nch;
             uint32_t va[16], vb[16];
             int u = sub;
-            if (u < units) tmem_ld16(tbase + (u / nch) * g.block_n + (u % nch) * 16, va);
+            auto unit_col = [&](int uu) { const int ii = (int)(((uint32_t)uu * g.nch_rcp) >> 16); return ii * g.block_n + (uu - ii * nch) * 16; };
+            if (u < units) tmem_ld16(tbase + unit_col(u), va);
             while (u < units)
             {
                 tmem_ld_wait();
                 int un = u + 4;
-                if (un < units) tmem_ld16(tbase + (un / nch) * g.block_n + (un % nch) * 16, vb);
+                if (un < units) tmem_ld16(tbase + unit_col(un), vb);
                 {
-                    const int i = u / nch, c = (u % nch) * 16;
+                    const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
                     epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
                 }
                 u = un;
                 if (u >= units) break;
                 tmem_ld_wait();
                 un = u + 4;
-                if (un < units) tmem_ld16(tbase + (un / nch) * g.block_n + (un % nch) * 16, va);
+                if (un < units) tmem_ld16(tbase + unit_col(un), va);
                 {
-                    const int i = u / nch, c = (u % nch) * 16;
+                    const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
                     epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
                 }
                 u = un;
@@ -290,10 +340,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int total_vec = mtc * 32 * nch;
             for (int vi = tq; vi < total_vec; vi += 128)
             {
-                const int lr = g.vshift >= 0 ? (vi >> g.vshift) : (vi / nch);
+                const int lr = (int)(((uint32_t)vi * g.nch_rcp) >> 16);
                 const int cv = vi - lr * nch;
-                const long long grow = (mt0 + (lr >> 5)) * BLOCK_M + q * 32 + (lr & 31);
-                if (grow < g.m && n0 + cv * 16 < g.ocp)
+                const long long grow = row_pixel(g, mt0 + (lr >> 5), q * 32 + (lr & 31));
+                if (grow >= 0 && n0 + cv * 16 < g.ocp)
                     *reinterpret_cast<uint4*>(out + (size_t)grow * g.ldo + n0 + cv * 16) = lds_u4(ost_s + (uint32_t)(lr * opitch + cv * 16));
             }
         }
@@ -356,6 +406,7 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
                      int variant)
 {
     if (m <= 0 || k <= 0 || (k & 15) || (ocp & 15) || (lda & 15) || (ldo & 15)) return TB200_ERR_INVALID;
+    memset(p, 0, sizeof *p);
     p->m = m, p->k = k, p->oc = oc, p->ocp = ocp, p->ldo = ldo, p->variant = variant;
     p->block_k = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     p->swizzle = p->block_k;
@@ -380,18 +431,72 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
     return rc;
 }
 
+// Implicit-GEMM plan for a dense (group 1, dilation 1) convolution with any kernel size and stride 1 or 2:
+// A = 4-D tensor map (C, W, H, N) over the NHWC input with traversal strides (1, s, s, 1); B = [OCp][taps*Cp].
+int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const ConvShape& s)
+{
+    if (s.group != 1 || s.dh != 1 || s.dw != 1 || s.sh != s.sw || (s.sh != 1 && s.sh != 2)) return TB200_ERR_UNSUPPORTED;
+    const int taps = s.kh * s.kw;
+    if (taps > 1 && (s.cp % 32)) return TB200_ERR_UNSUPPORTED; // a k-block must not straddle two taps
+    memset(p, 0, sizeof *p);
+    p->conv = 1;
+    p->m = (long long)s.n * s.oh * s.ow, p->oc = s.oc, p->ocp = s.ocp, p->ldo = s.ocp, p->variant = 0;
+    if (taps == 1) p->block_k = s.cp <= 32 ? 32 : (s.cp <= 64 ? 64 : 128);
+    else p->block_k = (s.cp % 128 == 0) ? 128 : ((s.cp % 64 == 0) ? 64 : 32);
+    p->swizzle = p->block_k;
+    p->cblocks = (s.cp + p->block_k - 1) / p->block_k;
+    p->k_blocks = taps * p->cblocks;
+    p->k = taps * s.cp;
+    p->block_n = s.ocp <= 256 ? s.ocp : 128;
+    p->n_tiles = (s.ocp + p->block_n - 1) / p->block_n;
+    // output patch of one m-tile: whole rows when they fit (then the patch is contiguous in the NHWC output)
+    if (s.ow <= BLOCK_M)
+    {
+        p->bw = s.ow;
+        p->bh = BLOCK_M / s.ow < s.oh ? BLOCK_M / s.ow : s.oh;
+        p->bn = (p->bh == s.oh) ? BLOCK_M / (s.ow * s.oh) : 1;
+        if (p->bn > s.n) p->bn = s.n;
+        if (p->bn < 1) p->bn = 1;
+    }
+    else
+        p->bw = BLOCK_M, p->bh = 1, p->bn = 1;
+    p->tiles_w = (s.ow + p->bw - 1) / p->bw;
+    p->tiles_h = (s.oh + p->bh - 1) / p->bh;
+    const long long tiles_n = (s.n + p->bn - 1) / p->bn;
+    p->m_tiles = (long long)p->tiles_w * p->tiles_h * tiles_n;
+    p->kw_n = s.kw, p->pad_h = s.ph0, p->pad_w = s.pw0, p->cstride = s.sh, p->cp = s.cp, p->oh = s.oh, p->ow = s.ow, p->nimg = s.n;
+    p->a_tx_bytes = (uint32_t)(p->block_k * p->bw * p->bh * p->bn);
+    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->block_n * p->block_k + 1023) & ~1023;
+    p->mt = 1;
+    if (p->n_tiles == 1)
+        while (p->mt < 4 && 2 * (p->mt * 2) * p->block_n <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+    const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
+    int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return TB200_ERR_INVALID;
+    p->stages = stages;
+    const uint64_t dims[4] = {(uint64_t)s.cp, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
+    const uint64_t strides[3] = {(uint64_t)s.cp, (uint64_t)s.w * s.cp, (uint64_t)s.h * s.w * s.cp};
+    const uint32_t box[4] = {(uint32_t)p->block_k, (uint32_t)((p->bw - 1) * s.sw + 1), (uint32_t)((p->bh - 1) * s.sh + 1), (uint32_t)p->bn};
+    const uint32_t estr[4] = {1u, (uint32_t)s.sw, (uint32_t)s.sh, 1u};
+    if (box[1] > 256 || box[2] > 256 || box[3] > 256) return TB200_ERR_UNSUPPORTED;
+    int rc = tmap_encode(p->tmap_a, in, 4, dims, strides, box, estr, p->swizzle);
+    if (rc) return rc;
+    return encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)s.ocp, (uint64_t)p->k, p->block_k, p->block_n, p->swizzle);
+}
+
 cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int num_sms, cudaStream_t st)
 {
     GemmArgs g;
-    g.m = p.m, g.m_tiles = p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
+    g.m = p.m, g.m_tiles = (int)p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
+    g.conv = p.conv, g.cblocks = p.cblocks, g.kw_n = p.kw_n, g.pad_h = p.pad_h, g.pad_w = p.pad_w, g.cstride = p.cstride, g.cp = p.cp;
+    g.bw = p.bw, g.bh = p.bh, g.bn = p.bn, g.tiles_w = p.tiles_w, g.tiles_h = p.tiles_h, g.oh = p.oh, g.ow = p.ow, g.nimg = p.nimg;
+    g.a_tx_bytes = p.a_tx_bytes;
     g.mt = p.mt;
-    g.num_super = ((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles;
-    {
-        const int nch = p.block_n >> 4;
-        g.vshift = -1;
-        for (int sh = 0; sh < 5; sh++)
-            if ((1 << sh) == nch) g.vshift = sh;
-    }
+    g.num_super = (int)(((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles);
+    g.nch_rcp = (65536u + (uint32_t)(p.block_n >> 4) - 1) / (uint32_t)(p.block_n >> 4);
+    g.bw_rcp = p.conv ? (65536u + (uint32_t)p.bw - 1) / (uint32_t)p.bw : 0;
+    g.bh_rcp = p.conv ? (65536u + (uint32_t)p.bh - 1) / (uint32_t)p.bh : 0;
     g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp, g.ldo = p.ldo;
     g.idesc = make_idesc_i8(p.block_n, !e.is_uint8, !e.is_uint8);
     uint32_t cols = 32;

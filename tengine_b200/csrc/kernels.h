@@ -66,6 +66,9 @@ struct GemmPlan
     int ldo;     // output row pitch in bytes
     int block_n, block_k, stages, k_blocks, n_tiles;
     int mt; // m-tiles per accumulator stage
+    // conv mode (implicit GEMM over a 4-D tensor map)
+    int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp, bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
+    unsigned a_tx_bytes;
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
     int variant; // debug: descriptor variant selector (0 = default)
@@ -73,6 +76,7 @@ struct GemmPlan
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
 int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
                      int variant);
+int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, const ConvShape& s);
 cudaError_t launch_gemm_i8(const GemmPlan& plan, void* out, const EpiParams& e, int num_sms, cudaStream_t st);
 
 } // namespace tb200

@@ -19,13 +19,15 @@ template <bool U8, int OCT>
 __global__ void __launch_bounds__(128) conv_direct_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wgt,
                                                           uint8_t* __restrict__ out, const ConvShape s, const __grid_constant__ EpiParams e)
 {
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)s.n * s.oh * s.ow;
+    // 32-bit index math (the launcher guarantees n*oh*ow < 2^31): 64-bit divisions cost ~100 instructions each
+    const unsigned pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned npix = (unsigned)s.n * s.oh * s.ow;
     if (pix >= npix) return;
     const int oc0 = blockIdx.y * OCT;
-    const int ow = (int)(pix % s.ow);
-    const int oh = (int)((pix / s.ow) % s.oh);
-    const int n = (int)(pix / ((long long)s.ow * s.oh));
+    const unsigned prow = pix / (unsigned)s.ow;
+    const int ow = (int)(pix - prow * s.ow);
+    const int n = (int)(prow / (unsigned)s.oh);
+    const int oh = (int)(prow - (unsigned)n * s.oh);
     const int og = s.oc / s.group;              // logical out channels per group
     const int g = (oc0 < s.oc) ? oc0 / og : 0;  // OCT divides og or group == 1 (host guarantees)
     const int cin0 = g * s.cg;                  // first logical input channel of the group
@@ -95,14 +97,15 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const uint8_t* __restrict_
                                                       uint8_t* __restrict__ out, const ConvShape s, const __grid_constant__ EpiParams e)
 {
     const int cw = s.cp / 4; // channel words per pixel
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)s.n * s.oh * s.ow * cw;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
+    const unsigned total = (unsigned)(s.n * s.oh * s.ow * cw);
     if (idx >= total) return;
-    const int c4 = (int)(idx % cw);
-    const long long pix = idx / cw;
-    const int ow = (int)(pix % s.ow);
-    const int oh = (int)((pix / s.ow) % s.oh);
-    const int n = (int)(pix / ((long long)s.ow * s.oh));
+    const unsigned pix = idx / (unsigned)cw;
+    const int c4 = (int)(idx - pix * cw);
+    const unsigned prow = pix / (unsigned)s.ow;
+    const int ow = (int)(pix - prow * s.ow);
+    const int n = (int)(prow / (unsigned)s.oh);
+    const int oh = (int)(prow - (unsigned)n * s.oh);
 
     int acc[4] = {0, 0, 0, 0};
     for (int kh = 0; kh < s.kh; kh++)
@@ -150,15 +153,15 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
 {
     const int cw = s.cp / 4;
     const int gpr = (s.ow + TW - 1) / TW; // pixel groups per output row
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)s.n * s.oh * gpr * cw;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
+    const unsigned total = (unsigned)(s.n * s.oh * gpr * cw);
     if (idx >= total) return;
-    const int c4 = (int)(idx % cw);
-    long long r = idx / cw;
-    const int pg = (int)(r % gpr);
-    r /= gpr;
-    const int oh = (int)(r % s.oh);
-    const int n = (int)(r / s.oh);
+    unsigned r = idx / (unsigned)cw;
+    const int c4 = (int)(idx - r * cw);
+    const unsigned r2 = r / (unsigned)gpr;
+    const int pg = (int)(r - r2 * gpr);
+    const int n = (int)(r2 / (unsigned)s.oh);
+    const int oh = (int)(r2 - (unsigned)n * s.oh);
     const int ow0 = pg * TW;
 
     int wj[9][4];
@@ -263,12 +266,13 @@ __global__ void __launch_bounds__(128, (OCT == 32 && !U8) ? 4 : 2)
         stem_w[i] = __ldg(reinterpret_cast<const int*>(wgt) + (size_t)(oc0 + j) * taps_total + t);
     }
     __syncthreads();
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)s.n * s.oh * s.ow;
+    const unsigned pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned npix = (unsigned)s.n * s.oh * s.ow;
     if (pix >= npix) return;
-    const int ow = (int)(pix % s.ow);
-    const int oh = (int)((pix / s.ow) % s.oh);
-    const int n = (int)(pix / ((long long)s.ow * s.oh));
+    const unsigned prow = pix / (unsigned)s.ow;
+    const int ow = (int)(pix - prow * s.ow);
+    const int n = (int)(prow / (unsigned)s.oh);
+    const int oh = (int)(prow - (unsigned)n * s.oh);
     const size_t plane = (size_t)s.h * s.w;
     const uint8_t* img = in + (size_t)n * s.c * plane;
 
@@ -346,14 +350,15 @@ template <bool U8>
 __global__ void __launch_bounds__(256) pool_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, PoolShape p)
 {
     const int cw = p.cp / 4;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.n * p.oh * p.ow * cw;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
+    const unsigned total = (unsigned)(p.n * p.oh * p.ow * cw);
     if (idx >= total) return;
-    const int c4 = (int)(idx % cw);
-    const long long pix = idx / cw;
-    const int pw = (int)(pix % p.ow);
-    const int ph = (int)((pix / p.ow) % p.oh);
-    const int n = (int)(pix / ((long long)p.ow * p.oh));
+    const unsigned pix = idx / (unsigned)cw;
+    const int c4 = (int)(idx - pix * cw);
+    const unsigned prow = pix / (unsigned)p.ow;
+    const int pw = (int)(pix - prow * p.ow);
+    const int n = (int)(prow / (unsigned)p.oh);
+    const int ph = (int)(prow - (unsigned)n * p.oh);
 
     int h_start = ph * p.sh - p.ph0, h_end = h_start + p.kh;
     if (h_end > p.h + p.ph0) h_end = p.h + p.ph0;
@@ -491,11 +496,11 @@ __global__ void __launch_bounds__(256) concat_kernel(const uint8_t* __restrict__
                                                      long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
                                                      int z_in, float s_out, int z_out)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix * c) return;
-    const int ch = (int)(idx % c);
-    const long long pix = idx / c;
-    const uint8_t v = in[pix * cp_in + ch];
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
+    if (idx >= (unsigned)(npix * c)) return;
+    const unsigned pix = idx / (unsigned)c;
+    const int ch = (int)(idx - pix * c);
+    const uint8_t v = in[(size_t)pix * cp_in + ch];
     int q;
     if (U8)
     {
@@ -507,19 +512,20 @@ __global__ void __launch_bounds__(256) concat_kernel(const uint8_t* __restrict__
         q = (int)roundf(__fmul_rn((float)(int)(int8_t)v, __fdiv_rn(s_in, s_out)));
         q = (q > 127 ? 127 : (q < -127 ? 127 : q)) & 0xff; // sic: concat_kernel_ref_int8.c:77-78
     }
-    out[pix * cp_out + c_off + ch] = (uint8_t)q;
+    out[(size_t)pix * cp_out + c_off + ch] = (uint8_t)q;
 }
 
 __global__ void __launch_bounds__(256) upsample_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int h,
                                                        int w, int cvec, int scale)
 {
     const int oh = h * scale, ow = w * scale;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n * oh * ow * cvec;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
+    const unsigned total = (unsigned)(n * oh * ow * cvec);
     if (idx >= total) return;
-    const int cv = (int)(idx % cvec);
-    const long long pix = idx / cvec;
-    const int x = (int)(pix % ow), y = (int)((pix / ow) % oh), b = (int)(pix / ((long long)ow * oh));
+    const unsigned pix = idx / (unsigned)cvec;
+    const int cv = (int)(idx - pix * cvec);
+    const unsigned prow = pix / (unsigned)ow;
+    const int x = (int)(pix - prow * ow), b = (int)(prow / (unsigned)oh), y = (int)(prow - (unsigned)b * oh);
     out[idx] = __ldg(in + (((size_t)b * h + y / scale) * w + x / scale) * cvec + cv);
 }
 
@@ -568,10 +574,13 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint8_t* __rest
 // Launchers
 // ------------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+#define TB200_CHECK_32BIT(total) \
+    if ((long long)(total) >= 2147483647LL) return cudaErrorInvalidValue // kernels index with 32 bits
 
 cudaError_t launch_conv_direct(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
 {
     const long long npix = (long long)s.n * s.oh * s.ow;
+    TB200_CHECK_32BIT(npix);
     const int og = s.oc / s.group;
     // OCT output channels per thread; with groups every tile must stay inside one group
     int oct = 8;
@@ -602,18 +611,18 @@ cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvS
         if (s.sh == 1)
         {
             constexpr int TW = 8;
-            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            const unsigned total = (unsigned)(s.n * s.oh * ((s.ow + TW - 1) / TW) * cw);
             conv_dw3x3_i8_kernel<TW, 1><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
         }
         else
         {
             constexpr int TW = 4;
-            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            const unsigned total = (unsigned)(s.n * s.oh * ((s.ow + TW - 1) / TW) * cw);
             conv_dw3x3_i8_kernel<TW, 2><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
         }
         return cudaGetLastError();
     }
-    const long long total = (long long)s.n * s.oh * s.ow * (s.cp / 4);
+    const unsigned total = (unsigned)(s.n * s.oh * s.ow * (s.cp / 4));
     if (e.is_uint8) conv_dw_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     else conv_dw_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     return cudaGetLastError();
@@ -622,6 +631,7 @@ cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvS
 cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
 {
     const long long npix = (long long)s.n * s.oh * s.ow;
+    TB200_CHECK_32BIT(npix);
     if (s.ocp % 32 == 0)
     {
         dim3 grid(blocks_for(npix, 128), s.ocp / 32);
@@ -639,7 +649,7 @@ cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const Con
 
 cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st)
 {
-    const long long total = (long long)p.n * p.oh * p.ow * (p.cp / 4);
+    const unsigned total = (unsigned)(p.n * p.oh * p.ow * (p.cp / 4));
     if (u8) pool_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     else pool_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     return cudaGetLastError();
@@ -657,6 +667,7 @@ cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c,
                                int z_in, float s_out, int z_out, bool u8, cudaStream_t st)
 {
     const long long total = npix * c;
+    TB200_CHECK_32BIT(total);
     if (u8) concat_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
     else concat_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
     return cudaGetLastError();
@@ -664,7 +675,7 @@ cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c,
 
 cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st)
 {
-    const long long total = (long long)n * h * scale * w * scale * (cp / 16);
+    const unsigned total = (unsigned)(n * h * scale * w * scale * (cp / 16));
     upsample_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, n, h, w, cp / 16, scale);
     return cudaGetLastError();
 }

@@ -21,15 +21,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~hint ns elapse, so a
+// waiting role does not burn issue slots that the epilogue warps of the same SM sub-partition need.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
     return ok != 0;
 }
@@ -37,10 +39,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait(bar, parity))
     {
-        if (clock64() - t0 > 4000000000LL) __trap(); // ~2 s
+        if (++spins > 2000000) __trap(); // > ~4 s of suspended waiting
     }
 }
 __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1)

@@ -196,3 +196,40 @@ def test_mobilenet_v1_int8_batch_properties(ctx, oracle):
         assert np.array_equal(y1[0], y64[i])
     gr.close()
     assert len(np.unique(y64)) > 50
+
+
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+@pytest.mark.parametrize("net", ["resnet50", "yolov3_tiny"])
+def test_reference_benchmark_graphs_every_layer(ctx, oracle, net, dtype):
+    """C3 / C4 of BASELINE.json at reduced width (same layer kinds, order and shapes' structure as the reference's
+    resnet50 / yolov3_tiny benchmark tmfiles): every layer against the oracle, bit-exact (uint8: exact-integer oracle)."""
+    if net == "resnet50":
+        g, b = workloads.resnet50(dtype, batch=2, res=96, width=0.25, classes=40, seed=5)
+    else:
+        g, b = workloads.yolov3_tiny(dtype, batch=2, res=96, width=0.25, head=27, seed=6)
+    x = b.random_input(2)
+    outs, tensors, kernels = _run_all_layers(ctx, g, x, abi.PRERUN_DEFAULT)
+    want = oracle.run(g, [x], uint8_mode=0)
+    for li, L in enumerate(g.layers):
+        assert np.array_equal(tensors[L["output"]], want[L["output"]]), f"{net} layer {li} {abi.OP_NAMES[L['op']]} ({kernels[li]})"
+
+
+def test_pipelined_run_equals_unpipelined(ctx):
+    """tb200_graph_run cuts the batch into chunks and overlaps H2D / kernels / D2H; same bytes as the single-chunk plan."""
+    import os
+    from tengine_b200 import runtime as rt
+
+    g, b = workloads.mobilenet_v1(abi.DT_INT8, batch=32, res=96, width=0.5, classes=50)
+    x = b.random_input(7)
+    outs = []
+    for chunks in ("1", "4", "2"):
+        os.environ["TB200_PIPELINE_CHUNKS"] = chunks
+        try:
+            gr = rt.Graph(ctx, g)
+            outs.append(gr.run([x])[0])
+            outs.append(gr.run([x])[0])  # twice: buffers are reused
+            gr.close()
+        finally:
+            os.environ.pop("TB200_PIPELINE_CHUNKS", None)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])

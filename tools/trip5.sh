@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+timeout 600 python bench.py --steps 20 --warmup 3 --cpu-images 0 > gpurun_out/bench_tc.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_i8|conv_dw3x3|conv_stem" -s 112 -c 28 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --cpu-images 0 > gpurun_out/ncu_all.log 2>&1
+grep -E "passed|failed" gpurun_out/pytest.log | tail -3; grep -E "^FAILED" gpurun_out/pytest.log | head -20; tail -n 1 gpurun_out/bench_tc.log
