@@ -526,16 +526,17 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
     int K = 1;
     if (same_batch && !(flags & TB200_PRERUN_NO_GRAPH))
     {
-        K = Ntot >= 64 ? 4 : (Ntot >= 16 ? 2 : 1);
+        K = Ntot >= 32 ? 2 : 1;
         if (const char* ev = getenv("TB200_PIPELINE_CHUNKS")) K = atoi(ev) > 0 ? atoi(ev) : K;
         while (K > 1 && Ntot % K) K--;
     }
-    g->chunks = K;
-    g->chunk_steps.resize(K);
-    const int nb = Ntot / K;
-    for (int ck = 0; ck < K; ck++)
+    const int Kpipe = K;
+    g->chunks = Kpipe;
+    g->chunk_steps.resize(Kpipe > 1 ? Kpipe : 0);
+    // builds the launch sequence of chunk `ck` of `K` (K == 1: the whole batch) into `steps`
+    auto build_steps = [&](const int K, const int ck, std::vector<Step>& steps, const bool count_work) -> int
     {
-        std::vector<Step>& steps = g->chunk_steps[ck];
+        const int nb = Ntot / K;
         auto tdev = [&](const TensorInfo& t) -> uint8_t* { return t.dev + (size_t)ck * (t.nhwc_bytes / K); };
         for (size_t i = 0; i < g->input_ids.size(); i++)
         {
@@ -591,6 +592,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 }
                 if (s.kind == K_CONV_STEM) s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
+                if (s.kind == K_IGEMM)
+                {
+                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.cs);
+                    if (rc) return bail(fail(rc, "layer %d: implicit-GEMM plan failed", li));
+                }
                 if (s.kind == K_GEMM)
                 {
                     const long long m = fc ? N : (long long)N * H * W;
@@ -665,28 +671,39 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             s.n = nb, s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
             steps.push_back(s);
         }
+        return 0;
+    };
+    // the whole-batch plan serves tb200_graph_launch / profile (device-resident use); the chunk plans serve the pipelined
+    // tb200_graph_run.  They address the same tensors (a chunk is a slice of dim 0), so either may run at any time.
+    {
+        int rc = build_steps(1, 0, g->steps, true);
+        if (rc) return rc;
+        for (int ck = 0; ck < (int)g->chunk_steps.size(); ck++)
+            if ((rc = build_steps(Kpipe, ck, g->chunk_steps[ck], false)) != 0) return rc;
     }
-    for (auto& cs : g->chunk_steps) g->steps.insert(g->steps.end(), cs.begin(), cs.end());
     g->num_launches = (int)g->steps.size();
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 
-    // ---- capture each chunk's launch sequence into a CUDA graph ----
+    // ---- capture the launch sequences into CUDA graphs: [0] = whole batch, [1..K] = the pipeline chunks ----
     if (!(flags & TB200_PRERUN_NO_GRAPH))
     {
-        g->cu_graphs.assign(K, nullptr);
-        g->cu_execs.assign(K, nullptr);
-        for (int ck = 0; ck < K; ck++)
+        const int ngraphs = 1 + (int)g->chunk_steps.size();
+        g->cu_graphs.assign(ngraphs, nullptr);
+        g->cu_execs.assign(ngraphs, nullptr);
+        for (int gi = 0; gi < ngraphs; gi++)
         {
+            const std::vector<Step>& seq = gi == 0 ? g->steps : g->chunk_steps[gi - 1];
             CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
-            for (const Step& s : g->chunk_steps[ck])
+            for (const Step& s : seq)
                 if ((rc = run_step(g, s, ctx->stream)) != 0) break;
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g->cu_graphs[ck]);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g->cu_graphs[gi]);
             if (rc) return bail(rc);
             if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)));
-            ce = cudaGraphInstantiate(&g->cu_execs[ck], g->cu_graphs[ck], 0);
+            ce = cudaGraphInstantiate(&g->cu_execs[gi], g->cu_graphs[gi], 0);
             if (ce != cudaSuccess) return bail(fail(TB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)));
         }
+        const int K = Kpipe;
         if (K > 1)
         {
             CUDA_OK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
@@ -721,7 +738,7 @@ int tb200_graph_launch(tb200_graph* g)
     CUDA_OK(cudaSetDevice(g->ctx->device));
     if (!g->cu_execs.empty())
     {
-        for (auto e : g->cu_execs) CUDA_OK(cudaGraphLaunch(e, g->ctx->stream));
+        CUDA_OK(cudaGraphLaunch(g->cu_execs[0], g->ctx->stream)); // the whole-batch graph
         return 0;
     }
     for (const Step& s : g->steps)
@@ -781,7 +798,7 @@ int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const*
     for (int ck = 0; ck < K; ck++)
     {
         CUDA_OK(cudaStreamWaitEvent(cs, g->ev_in[ck], 0));
-        CUDA_OK(cudaGraphLaunch(g->cu_execs[ck], cs));
+        CUDA_OK(cudaGraphLaunch(g->cu_execs[1 + ck], cs));
         CUDA_OK(cudaEventRecord(g->ev_out[ck], cs));
         CUDA_OK(cudaStreamWaitEvent(g->d2h_stream, g->ev_out[ck], 0));
         for (size_t i = 0; i < g->output_ids.size(); i++)

@@ -487,6 +487,7 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
 
 cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int num_sms, cudaStream_t st)
 {
+    if (p.block_n <= 0 || p.mt <= 0 || p.stages <= 0) return cudaErrorInvalidValue; // plan was never created
     GemmArgs g;
     g.m = p.m, g.m_tiles = (int)p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
     g.conv = p.conv, g.cblocks = p.cblocks, g.kw_n = p.kw_n, g.pad_h = p.pad_h, g.pad_w = p.pad_w, g.cstride = p.cstride, g.cp = p.cp;
