@@ -11,6 +11,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace tb200 {
 
 static constexpr int DW_THREADS = 128;
@@ -115,6 +117,134 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
         if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
 }
 
+// ---- stride-1 variant with three taps per dp4a ---------------------------------------------------------------
+// The dp4a / IMAD pipe is the busiest unit of the kernel above (9 dp4a per output).  Here each row of the window is
+// byte-transposed in registers (4 pixels x 4 channels -> 4 channel words, 8 PRMT on the ALU pipe), so that one dp4a
+// multiplies THREE horizontally adjacent taps of one channel: 3 dp4a + ~4.5 PRMT per output instead of 9 dp4a.
+__device__ __forceinline__ void transpose4x4(unsigned x0, unsigned x1, unsigned x2, unsigned x3, unsigned (&ch)[4])
+{
+    const unsigned t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x2, x3, 0x5140); // [a0 b0 a1 b1] [c0 d0 c1 d1]
+    const unsigned t2 = __byte_perm(x0, x1, 0x7362), t3 = __byte_perm(x2, x3, 0x7362); // [a2 b2 a3 b3] [c2 d2 c3 d3]
+    ch[0] = __byte_perm(t0, t1, 0x5410), ch[1] = __byte_perm(t0, t1, 0x7632);
+    ch[2] = __byte_perm(t2, t3, 0x5410), ch[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 6)
+    conv_dw3x3_tma_pack3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out,
+                                const ConvShape s, const __grid_constant__ EpiParams e, const int rows_per_cta, const int gpr,
+                                const int tile_cols, const int tile_rows)
+{
+    constexpr int TW = 8;
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int chunk = blockIdx.x;
+    const int oh0 = blockIdx.y * rows_per_cta;
+    const int n = blockIdx.z;
+    const int word = threadIdx.x & 7;
+    const int pg = threadIdx.x >> 3;
+    const int r = pg / gpr, gi = pg - r * gpr;
+    const int oh = oh0 + r, ow0 = gi * TW;
+    const int c4 = chunk * 8 + word;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        mbar_expect_tx(&bar, (uint32_t)(tile_rows * tile_cols * DW_CH));
+        tma_load_4d(&tmap_in, &bar, dw_smem, chunk * DW_CH, -s.pw0, oh0 - s.ph0, n);
+    }
+    const bool active = (r < rows_per_cta) && (oh < s.oh) && (ow0 < s.ow) && (c4 * 4 < s.cp);
+    unsigned wr[3][4]; // per filter row and channel: [w(kh,0), w(kh,1), w(kh,2), 0]
+    float m[4];
+    int32_t b[4];
+    if (active)
+    {
+#pragma unroll
+        for (int kh = 0; kh < 3; kh++)
+        {
+            const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(wgt + (size_t)(kh * 3 + 0) * s.cp) + c4);
+            const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(wgt + (size_t)(kh * 3 + 1) * s.cp) + c4);
+            const unsigned w2 = __ldg(reinterpret_cast<const unsigned*>(wgt + (size_t)(kh * 3 + 2) * s.cp) + c4);
+            unsigned tr[4];
+            transpose4x4(w0, w1, w2, 0u, tr);
+#pragma unroll
+            for (int j = 0; j < 4; j++) wr[kh][j] = tr[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const float2 p = e.fast_ok ? __ldg(e.fast_par + c4 * 4 + j) : make_float2(0.f, 0.f);
+            m[j] = p.x, b[j] = __float_as_int(p.y);
+        }
+    }
+    mbar_wait(&bar, 0);
+    if (!active) return;
+
+    int acc[TW][4];
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[t][j] = 0;
+    const uint32_t base = smem_u32(dw_smem) + (uint32_t)((r * tile_cols + ow0) * DW_CH + word * 4);
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+    {
+        unsigned xv[10];
+#pragma unroll
+        for (int col = 0; col < 10; col++)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xv[col]) : "r"(base + (uint32_t)((kh * tile_cols + col) * DW_CH)));
+        unsigned pa[4], pb[4];
+        transpose4x4(xv[0], xv[1], xv[2], xv[3], pa); // channel j: pixels 0..3
+        transpose4x4(xv[4], xv[5], xv[6], xv[7], pb); // channel j: pixels 4..7
+        const unsigned u0 = __byte_perm(xv[8], xv[9], 0x5140); // [i0 j0 i1 j1] (pixels 8, 9; channels 0, 1)
+        const unsigned u1 = __byte_perm(xv[8], xv[9], 0x7362); // [i2 j2 i3 j3]
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const unsigned w = wr[kh][j];
+            const unsigned uu = (j < 2) ? u0 : u1;
+            const unsigned s6 = (j & 1) ? 0x0632u : 0x0432u; // [P1.b2, P1.b3, pix8, -]
+            const unsigned s7 = (j & 1) ? 0x0763u : 0x0543u; // [P1.b3, pix8, pix9, -]
+            acc[0][j] = dp4a_s8((int)pa[j], (int)w, acc[0][j]);
+            acc[1][j] = dp4a_s8((int)__byte_perm(pa[j], pb[j], 0x4321), (int)w, acc[1][j]);
+            acc[2][j] = dp4a_s8((int)__byte_perm(pa[j], pb[j], 0x5432), (int)w, acc[2][j]);
+            acc[3][j] = dp4a_s8((int)__byte_perm(pa[j], pb[j], 0x6543), (int)w, acc[3][j]);
+            acc[4][j] = dp4a_s8((int)pb[j], (int)w, acc[4][j]);
+            acc[5][j] = dp4a_s8((int)(pb[j] >> 8), (int)w, acc[5][j]);
+            acc[6][j] = dp4a_s8((int)__byte_perm(pb[j], uu, s6), (int)w, acc[6][j]);
+            acc[7][j] = dp4a_s8((int)__byte_perm(pb[j], uu, s7), (int)w, acc[7][j]);
+        }
+    }
+
+    uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
+    if (!e.fast_ok)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
+        return;
+    }
+    uint32_t bad = 0;
+    uint32_t w[TW];
+#pragma unroll
+    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    if (bad)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((bad >> (t * 4 + j)) & 1u) w[t] = requant_fix_byte(w[t], j, acc[t][j], c4 * 4 + j, e);
+    }
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+}
+
 // Plan: tile geometry + the 4-D tensor map (C, W, H, N) of the input.  Returns 0, or <0 when this layer must use the
 // generic depthwise kernel (uint8, stride > 2, very wide rows ...).
 int dw_plan_create(DwPlan* p, const void* in, const ConvShape& s, const EpiParams& e)
@@ -145,7 +275,11 @@ cudaError_t launch_conv_dw_tma(const DwPlan& p, const void* w, void* out, const 
     dim3 grid((s.cp + DW_CH - 1) / DW_CH, (s.oh + p.rows_per_cta - 1) / p.rows_per_cta, s.n);
     CUtensorMap tm;
     memcpy(&tm, p.tmap_in, sizeof tm);
-    if (s.sh == 1)
+    static const bool pack3 = getenv("TB200_DW_NO_PACK3") == nullptr;
+    if (s.sh == 1 && pack3)
+        conv_dw3x3_tma_pack3_kernel<<<grid, DW_THREADS, p.smem_bytes, st>>>(tm, (const uint8_t*)w, (uint8_t*)out, s, e, p.rows_per_cta, p.gpr,
+                                                                           p.tile_cols, p.tile_rows);
+    else if (s.sh == 1)
         conv_dw3x3_tma_kernel<8, 1><<<grid, DW_THREADS, p.smem_bytes, st>>>(tm, (const uint8_t*)w, (uint8_t*)out, s, e, p.rows_per_cta, p.gpr,
                                                                             p.tile_cols, p.tile_rows);
     else

@@ -572,7 +572,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 {
                     cs.kh = H, cs.kw = W, cs.sh = cs.sw = 1, cs.ph0 = cs.pw0 = 0, cs.dh = cs.dw = 1, cs.group = 1;
                     cs.cg = C, cs.cgp = tin.cp;
-                    if (ck == 0)
+                    if (count_work)
                     {
                         g->work_ops += 2.0 * Ntot * OC * C * H * W;
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * C * H * W + (L.bias ? 4.0 * OC : 0);
@@ -584,7 +584,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     cs.dh = L.dilation_h, cs.dw = L.dilation_w, cs.group = L.group;
                     cs.cg = C / L.group, cs.cgp = (L.group == 1) ? tin.cp : cs.cg;
                     const double k = (double)cs.cg * cs.kh * cs.kw;
-                    if (ck == 0)
+                    if (count_work)
                     {
                         g->work_ops += 2.0 * (double)tout.nchw_bytes * k;
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
