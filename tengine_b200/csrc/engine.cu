@@ -75,6 +75,7 @@ struct Step
     PointwiseParams pp{};
     EpiParams epi{};
     GemmPlan gemm{};
+    const int32_t* btab = nullptr; // uint8 tensor-core kinds: padding-tap corrections
     DwPlan dwp{};
     long long bytes = 0; // pointwise / copy
     // concat / layout
@@ -244,9 +245,16 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
     return e;
 }
 
+// bytes of the packed B operand of the tensor-core paths: [n_tiles][block_n (+16 for uint8: the ones-row)][K]
+static size_t gemm_weight_bytes(int ocp, int k, bool u8)
+{
+    const int bn = gemm_block_n(ocp, u8), nt = (ocp + bn - 1) / bn;
+    return (size_t)nt * (bn + (u8 ? 16 : 0)) * k;
+}
+
 struct WeightBlob
 {
-    size_t w_off, bias_off, scale_off, fast_off, w_size;
+    size_t w_off, bias_off, scale_off, fast_off, btab_off, w_size;
 };
 
 static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
@@ -262,7 +270,7 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
         break;
     case K_CONV_DIRECT: err = launch_conv_direct(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_GEMM:
-    case K_IGEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, g->ctx->num_sms, st); break;
+    case K_IGEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, s.btab, g->ctx->num_sms, st); break;
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
     case K_POINTWISE: err = launch_pointwise(s.in, s.in2, s.out, s.bytes, s.pp, s.u8, st); break;
     case K_CONCAT_PART:
@@ -367,13 +375,13 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 kind[li] = K_CONV_STEM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * 4;
             else if (L.group == C && OC == C && C > 1)
                 kind[li] = K_CONV_DW, wsize = (size_t)L.kernel_h * L.kernel_w * tin.cp;
-            else if (!no_tc && !u8 && L.group == 1 && L.kernel_h == 1 && L.kernel_w == 1 && L.stride_h == 1 && L.stride_w == 1 &&
-                     !L.pad_h0 && !L.pad_h1 && !L.pad_w0 && !L.pad_w1)
-                kind[li] = K_GEMM, wsize = (size_t)tout.cp * tin.cp;
-            else if (!no_tc && !u8 && L.group == 1 && L.dilation_h == 1 && L.dilation_w == 1 && L.stride_h == L.stride_w &&
+            else if (!no_tc && L.group == 1 && L.kernel_h == 1 && L.kernel_w == 1 && L.stride_h == 1 && L.stride_w == 1 &&
+                     !L.pad_h0 && !L.pad_h1 && !L.pad_w0 && !L.pad_w1 && !(u8 && getenv("TB200_NO_U8_TC")))
+                kind[li] = K_GEMM, wsize = gemm_weight_bytes(tout.cp, tin.cp, u8);
+            else if (!no_tc && L.group == 1 && L.dilation_h == 1 && L.dilation_w == 1 && L.stride_h == L.stride_w &&
                      (L.stride_h == 1 || L.stride_h == 2) && (L.kernel_h * L.kernel_w == 1 || tin.cp % 32 == 0) && tout.d.dims[3] <= 4096 &&
-                     !getenv("TB200_NO_IGEMM"))
-                kind[li] = K_IGEMM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * tin.cp; // same packing as the direct kernel
+                     L.kernel_h * L.kernel_w <= 64 && !getenv("TB200_NO_IGEMM") && !(u8 && getenv("TB200_NO_U8_TC")))
+                kind[li] = K_IGEMM, wsize = gemm_weight_bytes(tout.cp, L.kernel_h * L.kernel_w * tin.cp, u8);
             else
             {
                 if (L.group > 1 && ((cg % 4) || ((OC / L.group) % 4)))
@@ -386,11 +394,10 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         else if (L.op == TB200_OP_FC)
         {
             if (!L.weight || !L.weight_scales) return bail(fail(TB200_ERR_INVALID, "layer %d: fc without weight/scales", li));
-            if (no_tc || u8)
-                kind[li] = K_CONV_DIRECT; // FC == conv with kernel HxW over the whole input
+            if (no_tc || (u8 && getenv("TB200_NO_U8_TC")))
+                kind[li] = K_CONV_DIRECT, blobs[li].w_size = (size_t)tout.cp * H * W * tin.cp; // FC == conv with kernel HxW over the whole input
             else
-                kind[li] = K_GEMM;
-            blobs[li].w_size = (size_t)tout.cp * H * W * tin.cp;
+                kind[li] = K_GEMM, blobs[li].w_size = gemm_weight_bytes(tout.cp, H * W * tin.cp, u8);
         }
         else if (L.op == TB200_OP_POOL)
             kind[li] = K_POOL;
@@ -424,6 +431,9 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             wtotal += align_up((size_t)tout.cp * 4, 256);
             blobs[li].fast_off = wtotal;
             wtotal += align_up((size_t)tout.cp * 8, 256);
+            blobs[li].btab_off = wtotal;
+            if (u8 && (kind[li] == K_GEMM || kind[li] == K_IGEMM))
+                wtotal += align_up((size_t)(L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w) * tout.cp * 4, 256);
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
@@ -466,12 +476,18 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             const int C = tin.d.dims[1], H = tin.d.dims[2], W = tin.d.dims[3], OC = tout.d.dims[1];
             const uint8_t* src = (const uint8_t*)L.weight;
             uint8_t* dst = img.data() + blobs[li].w_off;
+            const bool tc = kind[li] == K_GEMM || kind[li] == K_IGEMM;
+            // row of output channel o in the packed B operand (uint8 tensor-core tiles carry 16 extra rows each)
+            const int bn = tc ? gemm_block_n(tout.cp, u8) : tout.cp, bnx = bn + ((tc && u8) ? 16 : 0);
+            auto brow = [&](int o) -> size_t { return (size_t)(o / bn) * bnx + (o % bn); };
+            size_t krow = 0; // K extent of one packed row
             if (L.op == TB200_OP_FC)
             {
-                // [OC][C*H*W] (NCHW flatten, fc_ref.c:313-359) -> [OCp][H][W][Cp]
+                // [OC][C*H*W] (NCHW flatten, fc_ref.c:313-359) -> [row][H][W][Cp]
+                krow = (size_t)H * W * tin.cp;
                 for (int o = 0; o < OC; o++)
                     for (int c = 0; c < C; c++)
-                        for (int p = 0; p < H * W; p++) dst[((size_t)o * H * W + p) * tin.cp + c] = src[((size_t)o * C + c) * H * W + p];
+                        for (int p = 0; p < H * W; p++) dst[(brow(o) * H * W + p) * tin.cp + c] = src[((size_t)o * C + c) * H * W + p];
             }
             else
             {
@@ -484,11 +500,35 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 else
                 {
                     const int cgp = kind[li] == K_CONV_STEM ? 4 : (L.group == 1 ? tin.cp : cg);
+                    krow = (size_t)KH * KW * cgp;
                     for (int o = 0; o < OC; o++)
                         for (int c = 0; c < cg; c++)
                             for (int t = 0; t < KH * KW; t++)
-                                dst[((size_t)o * KH * KW + t) * cgp + c] = src[((size_t)o * cg + c) * KH * KW + t];
+                                dst[(brow(o) * KH * KW + t) * cgp + c] = src[((size_t)o * cg + c) * KH * KW + t];
                 }
+            }
+            std::vector<int64_t> wsum_tot(tout.cp, 0); // uint8 tensor-core kinds: sum of the raw weight bytes per channel
+            if (tc && u8)
+            {
+                // ones-row of every N tile: accumulator column block_n becomes sum_k x of the pixel
+                const int nt = (tout.cp + bn - 1) / bn;
+                for (int t = 0; t < nt; t++) memset(dst + ((size_t)t * bnx + bn) * krow, 1, krow);
+                // pad K positions (channels >= C) of the ones-row must not count: x is 0 there anyway (pad lanes hold 0)
+                const int taps = L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w;
+                const int kk = L.op == TB200_OP_FC ? C * H * W : C; // real K elements per tap
+                int32_t* bt = (int32_t*)(img.data() + blobs[li].btab_off);
+                for (int o = 0; o < OC; o++)
+                    for (int t = 0; t < taps; t++)
+                    {
+                        int64_t sw = 0;
+                        if (L.op == TB200_OP_FC)
+                            for (int k = 0; k < kk; k++) sw += src[(size_t)o * kk + k];
+                        else
+                            for (int c = 0; c < C; c++) sw += src[((size_t)o * C + c) * taps + t];
+                        wsum_tot[o] += sw;
+                        // what a tap that falls into the padding must give back: zx*(sum_c w - Cin*zw)
+                        bt[(size_t)t * tout.cp + o] = (int32_t)((int64_t)tin.d.zero_point * (sw - (int64_t)kk * L.weight_zero));
+                    }
             }
             int32_t* b = (int32_t*)(img.data() + blobs[li].bias_off);
             float* sc = (float*)(img.data() + blobs[li].scale_off);
@@ -503,7 +543,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     // the bias term in real units, rounded exactly as the reference rounds it
                     const float S = tin.d.scale * L.weight_scales[0];
                     fm[2 * o] = (o >= OC) ? 0.f : ((L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0]);
-                    fm[2 * o + 1] = 0.f;
+                    // tensor-core kinds: corr[oc] = -zx*sum_k w + K*zx*zw (all taps in bounds), carried in the .y lane
+                    int32_t corr = 0;
+                    if (tc && o < OC)
+                    {
+                        const int64_t kreal = fc ? (int64_t)C * H * W : (int64_t)C * L.kernel_h * L.kernel_w;
+                        corr = (int32_t)(-(int64_t)tin.d.zero_point * wsum_tot[o] + kreal * tin.d.zero_point * L.weight_zero);
+                    }
+                    memcpy(&fm[2 * o + 1], &corr, 4);
                 }
                 else
                 {
@@ -566,6 +613,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 s.epi.bias = (const int32_t*)(g->w_arena + blobs[li].bias_off);
                 s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
                 s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
+                s.btab = (const int32_t*)(g->w_arena + blobs[li].btab_off);
                 ConvShape& cs = s.cs;
                 cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
                 if (fc)
@@ -594,14 +642,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)
                 {
-                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.cs);
+                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.cs, u8 ? 1 : 0);
                     if (rc) return bail(fail(rc, "layer %d: implicit-GEMM plan failed", li));
                 }
                 if (s.kind == K_GEMM)
                 {
                     const long long m = fc ? N : (long long)N * H * W;
                     const int kdim = fc ? H * W * tin.cp : tin.cp;
-                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, m, kdim, OC, tout.cp, tout.cp, 0);
+                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 : 0);
                     if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
                 }
             }
@@ -939,10 +987,10 @@ int tb200k_gemm_i8(const void* in, const void* weight, void* out, int64_t m, int
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(TB200_ERR_NO_DEVICE, "no CUDA device");
     GemmPlan plan;
-    int rc = gemm_plan_create(&plan, in, k_pad, weight, m, k_pad, oc, cpad(oc), cpad(oc), 0);
+    int rc = gemm_plan_create(&plan, in, k_pad, weight, m, k_pad, oc, cpad(oc), cpad(oc), 0, 0);
     if (rc) return fail(rc, "gemm plan failed");
     EpiParams p = epi_from_abi(e);
-    K_LAUNCH(launch_gemm_i8(plan, out, p, sms, (cudaStream_t)stream));
+    K_LAUNCH(launch_gemm_i8(plan, out, p, nullptr, sms, (cudaStream_t)stream));
 }
 int tb200k_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, void* stream)
 {

@@ -22,6 +22,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace tb200 {
 
 static constexpr int BLOCK_M = 128;
@@ -72,6 +74,10 @@ struct GemmArgs
     int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp;
     int bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
     uint32_t a_tx_bytes; // bytes one A load delivers (block_k * rows of the patch)
+    // uint8: the B tile carries 16 extra rows, row block_n = all ones, so accumulator column block_n = sum_k x (per pixel)
+    int u8, bnx, taps, in_h, in_w;
+    int direct_store; // 1: each lane writes its 16 output bytes straight to global memory (no smem staging / copy-out)
+    const int32_t* btab; // [taps][OCp]: zx * (sum_c w[oc][tap][c] - Cin*zw), the correction a padding tap needs
 };
 
 // m-tile -> first output pixel coordinates (conv mode)
@@ -111,7 +117,7 @@ struct __align__(16) GemmSmemCtl
 __device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // 16 accumulator columns of one row -> 16 output bytes staged in shared memory
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, int oc0, int oc_limit,
+__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, uint8_t* gdst, int oc0, int oc_limit,
                                               const EpiParams& e)
 {
     uint32_t w[4];
@@ -146,7 +152,94 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
             if (oc0 + k < oc_limit) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], oc0 + k, e) & 0xffu) << (8 * (k & 3));
         }
     }
-    sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+    if (gdst) *reinterpret_cast<uint4*>(gdst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+}
+
+// uint8 flavour: v = sum x*w over in-bounds taps (raw bytes), sx = sum x.  The true accumulator is
+//   sum (x-zx)(w-zw) = v - zw*sx + corr[oc] + sum_{padding taps t} btab[t][oc]
+// with corr[oc] = -zx*sum_k w + taps*Cin*zx*zw (interior pixels) folded into the per-channel constants.
+__device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_t sx, uint64_t pad_mask, const GemmArgs& g, uint32_t par_addr,
+                                                 uint32_t dst_addr, uint8_t* gdst, int oc0, const EpiParams& e)
+{
+    const int32_t rowc = -e.w_zero * sx;
+    int32_t a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = (int32_t)v[k] + rowc;
+    if (pad_mask)
+    {
+        // border pixel: add the per-tap corrections of the taps that fell into the padding (rare rows)
+        for (int t = 0; t < g.taps; t++)
+            if ((pad_mask >> t) & 1ull)
+            {
+                const int32_t* bt = g.btab + (size_t)t * g.ocp + oc0;
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if (oc0 + k < g.ocp) a[k] += __ldg(bt + k);
+            }
+    }
+    uint32_t w[4];
+    if (e.fast_ok)
+    {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const float4 p01 = lds_f4(par_addr + j * 32);
+            const float4 p23 = lds_f4(par_addr + j * 32 + 16);
+            const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
+            const int32_t z4[4] = {0, 0, 0, 0};
+            // corr[oc] travels in the .y lanes
+            a[j * 4 + 0] += __float_as_int(p01.y), a[j * 4 + 1] += __float_as_int(p01.w);
+            a[j * 4 + 2] += __float_as_int(p23.y), a[j * 4 + 3] += __float_as_int(p23.w);
+            const int32_t a4[4] = {a[j * 4], a[j * 4 + 1], a[j * 4 + 2], a[j * 4 + 3]};
+            w[j] = requant_fast4<true>(a4, e, m4, z4, bad, 1u << (4 * j));
+        }
+        // pad lanes of uint8 tensors hold 0, not the zero point
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (oc0 + k >= g.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3))), bad &= ~(1u << k);
+        if (bad)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, a[k], oc0 + k, e);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            if ((k & 3) == 0) w[k >> 2] = 0;
+            if (oc0 + k < g.oc)
+            {
+                const float4 pp = lds_f4(par_addr + (k >> 1) * 16);
+                const int32_t corr = __float_as_int((k & 1) ? pp.w : pp.y);
+                w[k >> 2] |= ((uint32_t)requant(a[k] + corr, oc0 + k, e) & 0xffu) << (8 * (k & 3));
+            }
+        }
+    }
+    if (gdst) *reinterpret_cast<uint4*>(gdst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+}
+
+// taps of output pixel (oh, ow) that fall outside the image (bit t = kh*kw_n + kw)
+__device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int r)
+{
+    if (!g.conv || g.taps == 1 && g.pad_h == 0 && g.pad_w == 0) return 0;
+    int n0, oh0, ow0;
+    tile_origin(g, mt, n0, oh0, ow0);
+    const int t = (int)(((uint32_t)r * g.bw_rcp) >> 16), w = r - t * g.bw;
+    const int n = (int)(((uint32_t)t * g.bh_rcp) >> 16), h = t - n * g.bh;
+    const int iy0 = (oh0 + h) * g.cstride - g.pad_h, ix0 = (ow0 + w) * g.cstride - g.pad_w;
+    const int khn = g.taps / g.kw_n;
+    if (iy0 >= 0 && ix0 >= 0 && iy0 + khn <= g.in_h && ix0 + g.kw_n <= g.in_w) return 0; // interior
+    uint64_t m = 0;
+    for (int kh = 0; kh < khn; kh++)
+        for (int kw = 0; kw < g.kw_n; kw++)
+            if (iy0 + kh < 0 || iy0 + kh >= g.in_h || ix0 + kw < 0 || ix0 + kw >= g.in_w) m |= 1ull << (kh * g.kw_n + kw);
+    return m;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -157,7 +250,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // operand ring first (1024-byte aligned for the 128B swizzle), then the control block, the per-quarter epilogue
     // constants and the per-quarter output staging tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.block_n * g.block_k;
+    const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.bnx * g.block_k;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
     GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(smem + (size_t)g.stages * stage_bytes);
     const int opitch = g.block_n + OUT_PAD;
@@ -165,7 +258,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const uint32_t ost_base = par_base + 4u * (uint32_t)g.block_n * 8u;           // 4 x [mt*32][block_n + OUT_PAD]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int acc_cols = g.mt * g.block_n; // TMEM columns of one accumulator stage
+    const int acc_cols = g.mt * g.bnx; // TMEM columns of one accumulator stage
 
     if (threadIdx.x == 0)
     {
@@ -199,7 +292,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             {
                 const int msup = st / g.n_tiles;
                 const int mt0 = msup * g.mt;
-                const int n0 = (st - msup * g.n_tiles) * g.block_n;
+                const int ntile = st - msup * g.n_tiles;
+                const int n0 = ntile * g.bnx; // row of this N tile in the packed weight matrix
                 for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
                 {
                     const int m0 = (mt0 + i) * BLOCK_M;
@@ -248,7 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 tcgen05_fence_after();
                 for (int i = 0; i < g.mt && mt0 + i < g.m_tiles; i++)
                 {
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * acc_cols + i * g.block_n);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * acc_cols + i * g.bnx);
                     for (int kb = 0; kb < g.k_blocks; kb++)
                     {
                         mbar_wait(&ctl->full[stage], phase); // TMA bytes have landed
@@ -309,7 +403,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int units = mtc * nch;
             uint32_t va[16], vb[16];
             int u = sub;
-            auto unit_col = [&](int uu) { const int ii = (int)(((uint32_t)uu * g.nch_rcp) >> 16); return ii * g.block_n + (uu - ii * nch) * 16; };
+            auto unit_col = [&](int uu) { const int ii = (int)(((uint32_t)uu * g.nch_rcp) >> 16); return ii * g.bnx + (uu - ii * nch) * 16; };
             if (u < units) tmem_ld16(tbase + unit_col(u), va);
             while (u < units)
             {
@@ -318,7 +412,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (un < units) tmem_ld16(tbase + unit_col(un), vb);
                 {
                     const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
-                    epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
+                    uint8_t* gdst = nullptr;
+                    bool skip = false;
+                    if (g.direct_store)
+                    {
+                        const long long px = row_pixel(g, mt0 + i, q * 32 + lane);
+                        skip = px < 0 || n0 + c >= g.ocp;
+                        gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
+                    }
+                    int32_t sx = 0;
+                    if (g.u8) // warp-collective TMEM load: before any lane-dependent branch
+                    {
+                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
+                        tmem_ld_wait();
+                    }
+                    if (skip)
+                        ;
+                    else if (!g.u8)
+                        epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
+                    else
+                        epilogue_unit_u8(va, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
+                                         ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, e);
                 }
                 u = un;
                 if (u >= units) break;
@@ -327,7 +441,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (un < units) tmem_ld16(tbase + unit_col(un), va);
                 {
                     const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
-                    epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), n0 + c, g.oc, e);
+                    uint8_t* gdst = nullptr;
+                    bool skip = false;
+                    if (g.direct_store)
+                    {
+                        const long long px = row_pixel(g, mt0 + i, q * 32 + lane);
+                        skip = px < 0 || n0 + c >= g.ocp;
+                        gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
+                    }
+                    int32_t sx = 0;
+                    if (g.u8) // warp-collective TMEM load: before any lane-dependent branch
+                    {
+                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
+                        tmem_ld_wait();
+                    }
+                    if (skip)
+                        ;
+                    else if (!g.u8)
+                        epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
+                    else
+                        epilogue_unit_u8(vb, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
+                                         ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, e);
                 }
                 u = un;
             }
@@ -335,6 +469,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]); // accumulator drained: the MMA warp may overwrite it
             if (++as == 2) as = 0, aphase ^= 1;
+            if (g.direct_store) continue; // bytes already went to global memory
             quarter_bar_sync(5 + q); // B: the quarter's staged rows are complete
             // coalesced copy-out of this quarter's rows: consecutive threads write consecutive 16-byte pieces
             const int total_vec = mtc * 32 * nch;
@@ -402,8 +537,14 @@ static int encode_2d(void* tmap, const void* base, uint64_t inner, uint64_t rows
     return tmap_encode(tmap, base, 2, dims, strides, box, nullptr, swizzle);
 }
 
+int gemm_block_n(int ocp, int u8)
+{
+    if (!u8) return ocp <= 256 ? ocp : 128;
+    return ocp <= 240 ? ocp : 112; // +16 rows for the ones-row keeps the UMMA N at <= 256 / 128
+}
+
 int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
-                     int variant)
+                     int variant, int u8)
 {
     if (m <= 0 || k <= 0 || (k & 15) || (ocp & 15) || (lda & 15) || (ldo & 15)) return TB200_ERR_INVALID;
     memset(p, 0, sizeof *p);
@@ -411,15 +552,17 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
     p->block_k = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     p->swizzle = p->block_k;
     p->k_blocks = (k + p->block_k - 1) / p->block_k;
-    p->block_n = ocp <= 256 ? ocp : 128;
-    if (variant & 0x100) p->block_n = ocp <= 256 ? ocp : 256; // wide-N variant
+    p->u8 = u8;
+    p->block_n = gemm_block_n(ocp, u8);
+    p->bnx = p->block_n + (u8 ? 16 : 0);
+    p->taps = 1;
     p->n_tiles = (ocp + p->block_n - 1) / p->block_n;
     p->m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
-    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->block_n * p->block_k + 1023) & ~1023;
+    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->bnx * p->block_k + 1023) & ~1023;
     // m-tiles per accumulator stage: amortise the per-stage synchronisation over ~256 TMEM columns of work
     p->mt = 1;
     if (p->n_tiles == 1)
-        while (p->mt < 4 && 2 * (p->mt * 2) * p->block_n <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+        while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
     const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
     int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -427,13 +570,13 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
     p->stages = stages;
     int rc = encode_2d(p->tmap_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, p->block_k, BLOCK_M, p->swizzle);
     if (rc) return rc;
-    rc = encode_2d(p->tmap_b, b, (uint64_t)k, (uint64_t)ocp, (uint64_t)k, p->block_k, p->block_n, p->swizzle);
+    rc = encode_2d(p->tmap_b, b, (uint64_t)k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)k, p->block_k, p->bnx, p->swizzle);
     return rc;
 }
 
 // Implicit-GEMM plan for a dense (group 1, dilation 1) convolution with any kernel size and stride 1 or 2:
 // A = 4-D tensor map (C, W, H, N) over the NHWC input with traversal strides (1, s, s, 1); B = [OCp][taps*Cp].
-int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const ConvShape& s)
+int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const ConvShape& s, int u8)
 {
     if (s.group != 1 || s.dh != 1 || s.dw != 1 || s.sh != s.sw || (s.sh != 1 && s.sh != 2)) return TB200_ERR_UNSUPPORTED;
     const int taps = s.kh * s.kw;
@@ -447,7 +590,11 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
     p->cblocks = (s.cp + p->block_k - 1) / p->block_k;
     p->k_blocks = taps * p->cblocks;
     p->k = taps * s.cp;
-    p->block_n = s.ocp <= 256 ? s.ocp : 128;
+    p->u8 = u8;
+    p->block_n = gemm_block_n(s.ocp, u8);
+    p->bnx = p->block_n + (u8 ? 16 : 0);
+    p->taps = taps, p->in_h = s.h, p->in_w = s.w;
+    if (taps > 64) return TB200_ERR_UNSUPPORTED;
     p->n_tiles = (s.ocp + p->block_n - 1) / p->block_n;
     // output patch of one m-tile: whole rows when they fit (then the patch is contiguous in the NHWC output)
     if (s.ow <= BLOCK_M)
@@ -466,10 +613,10 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
     p->m_tiles = (long long)p->tiles_w * p->tiles_h * tiles_n;
     p->kw_n = s.kw, p->pad_h = s.ph0, p->pad_w = s.pw0, p->cstride = s.sh, p->cp = s.cp, p->oh = s.oh, p->ow = s.ow, p->nimg = s.n;
     p->a_tx_bytes = (uint32_t)(p->block_k * p->bw * p->bh * p->bn);
-    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->block_n * p->block_k + 1023) & ~1023;
+    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->bnx * p->block_k + 1023) & ~1023;
     p->mt = 1;
     if (p->n_tiles == 1)
-        while (p->mt < 4 && 2 * (p->mt * 2) * p->block_n <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+        while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
     const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
     int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -482,10 +629,10 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
     if (box[1] > 256 || box[2] > 256 || box[3] > 256) return TB200_ERR_UNSUPPORTED;
     int rc = tmap_encode(p->tmap_a, in, 4, dims, strides, box, estr, p->swizzle);
     if (rc) return rc;
-    return encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)s.ocp, (uint64_t)p->k, p->block_k, p->block_n, p->swizzle);
+    return encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)p->k, p->block_k, p->bnx, p->swizzle);
 }
 
-cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int num_sms, cudaStream_t st)
+cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st)
 {
     if (p.block_n <= 0 || p.mt <= 0 || p.stages <= 0) return cudaErrorInvalidValue; // plan was never created
     GemmArgs g;
@@ -493,17 +640,20 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, int
     g.conv = p.conv, g.cblocks = p.cblocks, g.kw_n = p.kw_n, g.pad_h = p.pad_h, g.pad_w = p.pad_w, g.cstride = p.cstride, g.cp = p.cp;
     g.bw = p.bw, g.bh = p.bh, g.bn = p.bn, g.tiles_w = p.tiles_w, g.tiles_h = p.tiles_h, g.oh = p.oh, g.ow = p.ow, g.nimg = p.nimg;
     g.a_tx_bytes = p.a_tx_bytes;
+    g.u8 = p.u8, g.bnx = p.bnx, g.taps = p.taps, g.in_h = p.in_h, g.in_w = p.in_w, g.btab = btab;
+    static const int direct_env = getenv("TB200_GEMM_DIRECT_STORE") ? atoi(getenv("TB200_GEMM_DIRECT_STORE")) : 0;
+    g.direct_store = direct_env;
     g.mt = p.mt;
     g.num_super = (int)(((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles);
     g.nch_rcp = (65536u + (uint32_t)(p.block_n >> 4) - 1) / (uint32_t)(p.block_n >> 4);
     g.bw_rcp = p.conv ? (65536u + (uint32_t)p.bw - 1) / (uint32_t)p.bw : 0;
     g.bh_rcp = p.conv ? (65536u + (uint32_t)p.bh - 1) / (uint32_t)p.bh : 0;
     g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp, g.ldo = p.ldo;
-    g.idesc = make_idesc_i8(p.block_n, !e.is_uint8, !e.is_uint8);
+    g.idesc = make_idesc_i8(p.bnx, !p.u8, !p.u8);
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * p.mt * p.block_n)) cols <<= 1;
+    while (cols < (uint32_t)(2 * p.mt * p.bnx)) cols <<= 1;
     g.tmem_cols = cols;
-    const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.block_n * p.block_k + 1023) & ~1023;
+    const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.bnx * p.block_k + 1023) & ~1023;
     const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + sizeof(GemmSmemCtl) + 4 * (size_t)p.block_n * 8 +
                         (size_t)BLOCK_M * p.mt * (p.block_n + OUT_PAD) + 1024;
     static bool attr_set = false;

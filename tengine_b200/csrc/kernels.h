@@ -69,14 +69,16 @@ struct GemmPlan
     // conv mode (implicit GEMM over a 4-D tensor map)
     int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp, bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
     unsigned a_tx_bytes;
+    int u8, bnx, taps, in_h, in_w; // uint8: B tiles carry 16 extra rows (ones-row -> per-pixel sum of x)
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
+int gemm_block_n(int ocp, int u8);
 int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
-                     int variant);
-int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, const ConvShape& s);
-cudaError_t launch_gemm_i8(const GemmPlan& plan, void* out, const EpiParams& e, int num_sms, cudaStream_t st);
+                     int variant, int u8);
+int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, const ConvShape& s, int u8);
+cudaError_t launch_gemm_i8(const GemmPlan& plan, void* out, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
 
 } // namespace tb200

@@ -101,21 +101,26 @@ GEMM_CASES = [
 
 
 @pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "n%d_k%d_%dx%d_oc%d" % c)
-@pytest.mark.parametrize("act,recipe", [(0, abi.RECIPE_HCL), (6, abi.RECIPE_REF), (-1, abi.RECIPE_HCL)])
-def test_tcgen05_gemm_1x1_bit_exact(ctx, oracle, case, act, recipe):
+@pytest.mark.parametrize("act,recipe,dtype", [(0, abi.RECIPE_HCL, abi.DT_INT8), (6, abi.RECIPE_REF, abi.DT_INT8),
+                                              (-1, abi.RECIPE_HCL, abi.DT_INT8), (0, abi.RECIPE_HCL, abi.DT_UINT8),
+                                              (-1, abi.RECIPE_REF, abi.DT_UINT8)])
+def test_tcgen05_gemm_1x1_bit_exact(ctx, oracle, case, act, recipe, dtype):
+    """uint8 runs the same UMMA with unsigned operands; the zero points are folded exactly (ones-row sum of x,
+    per-channel sum of w): bit-exact against the exact-integer oracle."""
     from tengine_b200 import runtime as rt
 
     n, c, h, w, oc = case
     rng = np.random.default_rng(sum(case))
-    g, x = _one_conv(rng, abi.DT_INT8, n, c, h, w, oc, 1, 1, 0, 1, act, recipe)
+    g, x = _one_conv(rng, dtype, n, c, h, w, oc, 1, 1, 0, 1, act, recipe)
     gr = rt.Graph(ctx, g)
     try:
         assert gr.layer_kernels() == ["gemm_i8_tcgen05"]
         got = gr.run([x])[0]
     finally:
         gr.close()
-    want = oracle.run(g, [x])[g.outputs[0]]
-    assert (np.abs(want.astype(int)) == 127).mean() < 0.3
+    want = oracle.run(g, [x], uint8_mode=0)[g.outputs[0]]
+    if dtype == abi.DT_INT8:
+        assert (np.abs(want.astype(int)) == 127).mean() < 0.3
     assert np.array_equal(got, want)
 
 
