@@ -242,6 +242,7 @@ __device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int 
     return m;
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                            uint8_t* __restrict__ out, const GemmArgs g, const __grid_constant__ EpiParams e)
@@ -421,14 +422,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
                     }
                     int32_t sx = 0;
-                    if (g.u8) // warp-collective TMEM load: before any lane-dependent branch
+                    if (U8) // warp-collective TMEM load: before any lane-dependent branch
                     {
                         sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
                         tmem_ld_wait();
                     }
                     if (skip)
                         ;
-                    else if (!g.u8)
+                    else if (!U8)
                         epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
                     else
                         epilogue_unit_u8(va, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
@@ -450,14 +451,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
                     }
                     int32_t sx = 0;
-                    if (g.u8) // warp-collective TMEM load: before any lane-dependent branch
+                    if (U8) // warp-collective TMEM load: before any lane-dependent branch
                     {
                         sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
                         tmem_ld_wait();
                     }
                     if (skip)
                         ;
-                    else if (!g.u8)
+                    else if (!U8)
                         epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
                     else
                         epilogue_unit_u8(vb, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
@@ -659,7 +660,9 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, con
     static bool attr_set = false;
     if (!attr_set)
     {
-        cudaError_t err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
@@ -667,7 +670,8 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, con
     CUtensorMap ta, tb;
     memcpy(&ta, p.tmap_a, sizeof ta);
     memcpy(&tb, p.tmap_b, sizeof tb);
-    gemm_i8_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, (uint8_t*)out, g, e);
+    if (p.u8) gemm_i8_tcgen05_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, (uint8_t*)out, g, e);
+    else gemm_i8_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, (uint8_t*)out, g, e);
     return cudaGetLastError();
 }
 
