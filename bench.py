@@ -87,17 +87,19 @@ def build_workload(name, batch):
     raise SystemExit(f"unknown workload {name}")
 
 
-def _ref_worker(workload, images, threads, q):
-    """One reference process: `images` batch-1 run_graph() calls on `threads` OpenMP threads."""
+def _ref_worker(graph_npz, images, threads, q):
+    """One reference process: `images` batch-1 run_graph() calls on `threads` OpenMP threads.  The quantised graph comes
+    from a file written by the parent, so the workers need neither torch nor a calibration pass."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle.pyoracle import Reference
+    from tengine_b200.graphdef import GraphDef
 
+    d = dict(np.load(graph_npz))
+    g = GraphDef.from_dict(d)
+    x = d["input"]
     ref = Reference()
-    g, b = build_workload(workload, 1)
-    x = b.random_input(1)
-    t0 = time.perf_counter()
     _, (mn, avg) = ref.run(g, [x], threads=threads, warmup=1, loops=images)
-    q.put((images, avg * images / 1000.0, mn, time.perf_counter() - t0))
+    q.put((images, avg * images / 1000.0, mn))
 
 
 def reference_cpu_rate(workload, images, threads_per_proc=8):
@@ -106,19 +108,31 @@ def reference_cpu_rate(workload, images, threads_per_proc=8):
     batched int8 path is slower and, for 3x3, wrong: SURVEY.md fact 8; one process does not scale past ~8 threads on
     these layer sizes).  Throughput = images / wall time of the slowest worker's timed loop."""
     import multiprocessing as mp
+    import tempfile
 
     cores = os.cpu_count() or 1
     t = min(threads_per_proc, cores)
     procs = max(1, cores // t)
     per = max(2, images // procs)
+    g, b = build_workload(workload, 1)
+    d = g.to_dict()
+    d["input"] = b.random_input(1)
+    tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
+    tmp.close()
+    np.savez(tmp.name, **d)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_ref_worker, args=(workload, per, t, q)) for _ in range(procs)]
+    ps = [ctx.Process(target=_ref_worker, args=(tmp.name, per, t, q)) for _ in range(procs)]
     for p in ps:
         p.start()
-    res = [q.get(timeout=600) for _ in ps]
-    for p in ps:
-        p.join(60)
+    try:
+        res = [q.get(timeout=280) for _ in ps]
+    finally:
+        for p in ps:
+            p.join(5)
+            if p.is_alive():
+                p.terminate()
+        os.unlink(tmp.name)
     loop_s = max(r[1] for r in res)
     rate = per * procs / loop_s
     sample = (f"{procs} processes x {t} threads, {per} batch-1 run_graph() each of {workload} "
