@@ -27,6 +27,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec int8 CNN inference (MobileNet-v1 224x224)"
 UNIT = "images/s"
+# name -> (builder, data type, resolution, default images per GPU, metric label)
+WORKLOADS = {
+    "mobilenet_v1_int8": ("mobilenet_v1", "int8", 224, 256, "images/sec int8 CNN inference (MobileNet-v1 224x224)"),
+    "mobilenet_v1_uint8": ("mobilenet_v1", "uint8", 224, 256, "images/sec uint8 CNN inference (MobileNet-v1 224x224)"),
+    "resnet50_uint8": ("resnet50", "uint8", 224, 512, "images/sec uint8 CNN inference (ResNet-50 224x224)"),
+    "resnet50_int8": ("resnet50", "int8", 224, 512, "images/sec int8 CNN inference (ResNet-50 224x224)"),
+    "yolov3_tiny_uint8": ("yolov3_tiny", "uint8", 416, 16, "images/sec uint8 CNN inference (YOLOv3-tiny 416x416)"),
+    "yolov3_tiny_int8": ("yolov3_tiny", "int8", 416, 16, "images/sec int8 CNN inference (YOLOv3-tiny 416x416)"),
+}
 
 
 def measured_peaks():
@@ -80,63 +89,63 @@ class ClockSampler(threading.Thread):
 def build_workload(name, batch):
     from tengine_b200 import abi, workloads
 
-    if name == "mobilenet_v1_int8":
-        return workloads.mobilenet_v1(abi.DT_INT8, batch=batch)
-    if name == "mobilenet_v1_uint8":
-        return workloads.mobilenet_v1(abi.DT_UINT8, batch=batch)
-    raise SystemExit(f"unknown workload {name}")
+    if name not in WORKLOADS:
+        raise SystemExit(f"unknown workload {name}; choose from {sorted(WORKLOADS)}")
+    builder, dt, res, _, _ = WORKLOADS[name]
+    return getattr(workloads, builder)(abi.DT_INT8 if dt == "int8" else abi.DT_UINT8, batch=batch, res=res)
 
 
-def _ref_worker(graph_npz, images, threads, q):
-    """One reference process: `images` batch-1 run_graph() calls on `threads` OpenMP threads.  The quantised graph comes
-    from a file written by the parent, so the workers need neither torch nor a calibration pass."""
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    from oracle.pyoracle import Reference
-    from tengine_b200.graphdef import GraphDef
-
-    d = dict(np.load(graph_npz))
-    g = GraphDef.from_dict(d)
-    x = d["input"]
-    ref = Reference()
-    _, (mn, avg) = ref.run(g, [x], threads=threads, warmup=1, loops=images)
-    q.put((images, avg * images / 1000.0, mn))
-
-
-def reference_cpu_rate(workload, images, threads_per_proc=8):
-    """images/s of the UNMODIFIED reference CPU backend (oracle/_ref) using every host core: P = cores/8 independent
-    processes x 8 OpenMP threads, each looping batch-1 run_graph() -- the reference's best case (its HCL kernels; its
-    batched int8 path is slower and, for 3x3, wrong: SURVEY.md fact 8; one process does not scale past ~8 threads on
-    these layer sizes).  Throughput = images / wall time of the slowest worker's timed loop."""
-    import multiprocessing as mp
+def reference_cpu_rate(workload, images, threads_per_proc=int(os.environ.get("TB200_REF_THREADS", "1")), budget_s=150.0):
+    """images/s of the UNMODIFIED reference CPU backend (oracle/_ref) using every host core this process may run on:
+    P = cores/T independent processes x T OpenMP threads (T = TB200_REF_THREADS, default 1), each pinned to its own
+    CPUs and looping batch-1 run_graph() -- the reference's best case for THROUGHPUT: its HCL kernels scale poorly with
+    threads on these layer sizes (measured on 8 cores, MobileNet-v1 int8: 8x1 threads 60.7 img/s, 4x2 58.1, 2x4 42.1,
+    1x8 22.5), its batched int8 path is slower and, for 3x3, wrong, and its cluster mask cannot
+    describe more than 64 CPUs (source/system/cpu.c:120-121,269).  Throughput = images / wall time of the slowest worker's timed loop.
+    Workers are plain subprocesses (python -m oracle.ref_worker) with a hard time budget; a worker that does not report
+    in time is killed by PID and the measurement fails loudly."""
+    import subprocess
     import tempfile
 
-    cores = os.cpu_count() or 1
-    t = min(threads_per_proc, cores)
-    procs = max(1, cores // t)
-    per = max(2, images // procs)
+    cpus = sorted(os.sched_getaffinity(0))
+    t = max(1, min(threads_per_proc, len(cpus)))
+    procs = max(1, len(cpus) // t)
+    per = max(4, images // procs)
     g, b = build_workload(workload, 1)
     d = g.to_dict()
     d["input"] = b.random_input(1)
     tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
     tmp.close()
     np.savez(tmp.name, **d)
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    ps = [ctx.Process(target=_ref_worker, args=(tmp.name, per, t, q)) for _ in range(procs)]
-    for p in ps:
-        p.start()
+    ps = []
     try:
-        res = [q.get(timeout=280) for _ in ps]
+        for i in range(procs):
+            env = dict(os.environ)
+            env["OMP_NUM_THREADS"] = str(t)
+            env["REF_SHIM_CPUS"] = ",".join(str(c) for c in cpus[i * t:(i + 1) * t])
+            env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+            ps.append(subprocess.Popen([sys.executable, "-m", "oracle.ref_worker", tmp.name, str(per), str(t)], cwd=ROOT,
+                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        deadline = time.time() + budget_s
+        res = []
+        for p in ps:
+            try:
+                out, err = p.communicate(timeout=max(1.0, deadline - time.time()))
+            except subprocess.TimeoutExpired:
+                raise RuntimeError(f"reference worker pid {p.pid} did not finish within {budget_s:.0f} s")
+            if p.returncode != 0:
+                raise RuntimeError(f"reference worker failed rc={p.returncode}: {err[-500:]}")
+            res.append(json.loads(out.strip().splitlines()[-1]))
     finally:
         for p in ps:
-            p.join(5)
-            if p.is_alive():
-                p.terminate()
+            if p.poll() is None:
+                p.kill()
+                p.wait()
         os.unlink(tmp.name)
-    loop_s = max(r[1] for r in res)
+    loop_s = max(r["loop_s"] for r in res)
     rate = per * procs / loop_s
-    sample = (f"{procs} processes x {t} threads, {per} batch-1 run_graph() each of {workload} "
-              f"(slowest loop {loop_s:.2f} s, best single-image latency {min(r[2] for r in res):.1f} ms)")
+    sample = (f"{procs} processes x {t} pinned threads, {per} batch-1 run_graph() each of {workload} "
+              f"(slowest loop {loop_s:.2f} s, best single-image latency {min(r['min_ms'] for r in res):.1f} ms)")
     return rate, procs * t, sample
 
 
@@ -150,13 +159,13 @@ def run_reference_arm(args, rank):
         r, cores, sample = reference_cpu_rate(args.workload, per_step)
         if s >= args.warmup:
             rates.append(r)
-        if time.time() - t0 > 240 and rates:
+        if time.time() - t0 > 150 and rates:
             break
     v = float(np.mean(rates))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(rates),
             "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": f"{args.workload} 224x224, reference CPU backend, {per_step} images per step (batch-1 runs)"},
+            "vs_baseline": None, "dtype": WORKLOADS[args.workload][1], "data": "synthetic",
+            "config": {"workload": f"{args.workload}, reference CPU backend, {per_step} images per step (batch-1 runs)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -169,12 +178,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="mobilenet_v1_int8")
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the workload's BASELINE.json batch)")
     ap.add_argument("--ref-images", type=int, default=256, help="reference arm: images per step (split over the worker processes)")
     ap.add_argument("--no-tensorcore", action="store_true", help="route convs through the CUDA-core cross-check kernels")
     ap.add_argument("--cpu-images", type=int, default=2048, help="cpu_baseline sample size (images over all workers); 0 disables")
     args = ap.parse_args()
 
+    if args.workload not in WORKLOADS:
+        raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(WORKLOADS)}")
+    if args.batch <= 0:
+        args.batch = WORKLOADS[args.workload][3]
+    global METRIC
+    METRIC = WORKLOADS[args.workload][4]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -291,11 +306,11 @@ def main():
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": WORKLOADS[args.workload][1],
             "data": "synthetic",
-            "config": {"workload": f"{args.workload} 224x224 batch={args.batch} per GPU (BASELINE.json configs[1])",
+            "config": {"workload": f"{args.workload} {WORKLOADS[args.workload][2]}x{WORKLOADS[args.workload][2]} batch={args.batch} per GPU" + (" (BASELINE.json configs[1])" if args.workload == "mobilenet_v1_int8" else ""),
                        "global_batch": args.batch * world, "parallelism": f"batch-sharded x{world}, weights broadcast once (NCCL) at prerun",
-                       "l2": "256 MiB L2 flush between timed iterations; per-step activations 2.6 GB >> 126 MB L2",
+                       "l2": "256 MiB L2 flush between timed iterations; per-step activations >> 126 MB L2",
                        "layout": "NHWC int8 in HBM, channels padded to 16"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(y.nbytes),
                     "ms_per_step": e2e_ms / args.steps, "api": "tb200_graph_run(host NCHW in, host NCHW out), pinned buffers"},

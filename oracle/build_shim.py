@@ -18,7 +18,7 @@ def main(ref, libdir):
     objd = os.path.join(libdir, "shim_obj")
     os.makedirs(objd, exist_ok=True)
     objs = []
-    jobs = [(os.path.join(HERE, "ref_shim.c"), [CC, "-std=gnu99"]),
+    jobs = [(os.path.join(HERE, "ref_shim.c"), [CC, "-std=gnu99", "-fopenmp"]),
             (os.path.join(HERE, "ref_shim_save.cpp"), [CXX, "-std=c++11", "-include", "cstdint"]),
             (f"{ref}/tools/save_graph/save_graph.cpp", [CXX, "-std=c++11", "-include", "cstdint"]),
             (f"{ref}/tools/save_graph/tm2_op_save.cpp", [CXX, "-std=c++11", "-include", "cstdint"]),
@@ -28,7 +28,7 @@ def main(ref, libdir):
         subprocess.check_call(comp + ["-O2", "-fPIC", "-w"] + inc + ["-c", src, "-o", o])
         objs.append(o)
     subprocess.check_call([CXX, "-shared", "-o", os.path.join(libdir, "libref_shim.so")] + objs +
-                          [f"-L{libdir}", "-ltengine-lite", "-Wl,-rpath,$ORIGIN"])
+                          [f"-L{libdir}", "-ltengine-lite", "-fopenmp", "-Wl,-rpath,$ORIGIN"])
 
 
 if __name__ == "__main__":

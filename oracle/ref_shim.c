@@ -1,3 +1,5 @@
+#define _GNU_SOURCE
+#include <sched.h>
 /*
  * ref_shim.c -- drive the UNMODIFIED reference (oracle/_ref/libtengine-lite.so) from this repo's layer
  * descriptors.  TEST INFRASTRUCTURE ONLY (see oracle/tb200_oracle.c header).
@@ -271,6 +273,34 @@ fail:
     return rc;
 }
 
+/* prerun_graph_multithread() ends with set_cpu_affine(mask) (source/api/c_api.c:540-547), which pins every OpenMP
+ * thread of the process to CPUs 0..omp_get_max_threads()-1.  Several reference processes on one host would then all
+ * sit on the same cores.  When REF_SHIM_CPUS="3,4,5" is set, the harness re-pins this process' OpenMP team to that
+ * CPU list after prerun (process placement only; the reference code is untouched). */
+static void repin_from_env(int num_thread)
+{
+    const char* cs = getenv("REF_SHIM_CPUS");
+    if (!cs || !*cs) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (const char* p = cs; *p;)
+    {
+        char* e;
+        long c = strtol(p, &e, 10);
+        if (e == p) break;
+        if (c >= 0 && c < CPU_SETSIZE) { CPU_SET((int)c, &set); n++; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e && *e != ',') break;
+    }
+    if (!n) return;
+    if (num_thread < 1) num_thread = 1;
+#pragma omp parallel num_threads(num_thread)
+    {
+        sched_setaffinity(0, sizeof(set), &set);
+    }
+}
+
 /* Returns 0 on success.  `want_ids` tensors (layer outputs) are marked graph outputs and returned in out_bufs.
  * ms_stats[0]=min, [1]=avg over `loops` timed run_graph calls (after `warmup`). */
 SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
@@ -296,6 +326,7 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
         rc = -103;
         goto done;
     }
+    repin_from_env(num_thread);
     /* the shapes the reference inferred must be the shapes the caller described */
     for (int i = 0; i < num_tensors; i++)
     {

@@ -37,6 +37,7 @@ struct EpiParams
     float fast_flo, fast_fhi; // uint8: activation clamp in real units
     float fast_r;             // uint8: fl(1/s_out)
     int32_t fast_ok;          // 0: scales are degenerate, always take the exact path
+    int32_t fuse_bias;        // int8 conv: fast_par[oc].y holds fl(bias*M) (a float) and t = fma((float)acc, M, .y); see requant_fast_bits
 };
 
 // C round(): half away from zero, exact for every float (CUDA's roundf is the exact, slow-path version).
@@ -139,11 +140,16 @@ static __device__ __noinline__ int requant(int32_t acc, int oc, const EpiParams&
 
 // One element: returns the bit pattern of r = t + MAGIC (low byte = the rounded, clamped integer) and ORs `bit` into
 // `bad` when t is inside the tie guard band.  ~10 instructions; U8 is a compile-time switch so no per-element branch.
-template <bool U8>
+// FUSE (int8 conv layers whose |bias*M| <= 100 output LSBs, decided at prerun): the integer bias add is folded into
+// an FMA, t = fma((float)acc, M, fl(bias*M)), one instruction less.  Extra error <= 2^-23*(|t| + |bias*M|) < 4.1e-5,
+// total |t - t_ref| < 6.4e-5 -- still inside the 2^-13 guard band, so exactness is preserved by the same argument.
+template <bool U8, bool FUSE = false>
 __device__ __forceinline__ uint32_t requant_fast_bits(int32_t acc, const EpiParams& e, float m, int32_t b, uint32_t& bad, uint32_t bit)
 {
     float t;
-    if (!U8)
+    if (!U8 && FUSE)
+        t = __fmaf_rn((float)acc, m, __int_as_float(b));
+    else if (!U8)
         t = __fmul_rn((float)(acc + b), m);
     else
     {
@@ -161,14 +167,14 @@ __device__ __forceinline__ uint32_t requant_fast_bits(int32_t acc, const EpiPara
 }
 
 // Four consecutive channels -> one packed 32-bit word (3 PRMT).  `bad` receives bits (bit0 << j) for guarded elements.
-template <bool U8>
+template <bool U8, bool FUSE = false>
 __device__ __forceinline__ uint32_t requant_fast4(const int32_t (&acc)[4], const EpiParams& e, const float (&m)[4], const int32_t (&b)[4],
                                                   uint32_t& bad, uint32_t bit0)
 {
-    const uint32_t r0 = requant_fast_bits<U8>(acc[0], e, m[0], b[0], bad, bit0);
-    const uint32_t r1 = requant_fast_bits<U8>(acc[1], e, m[1], b[1], bad, bit0 << 1);
-    const uint32_t r2 = requant_fast_bits<U8>(acc[2], e, m[2], b[2], bad, bit0 << 2);
-    const uint32_t r3 = requant_fast_bits<U8>(acc[3], e, m[3], b[3], bad, bit0 << 3);
+    const uint32_t r0 = requant_fast_bits<U8, FUSE>(acc[0], e, m[0], b[0], bad, bit0);
+    const uint32_t r1 = requant_fast_bits<U8, FUSE>(acc[1], e, m[1], b[1], bad, bit0 << 1);
+    const uint32_t r2 = requant_fast_bits<U8, FUSE>(acc[2], e, m[2], b[2], bad, bit0 << 2);
+    const uint32_t r3 = requant_fast_bits<U8, FUSE>(acc[3], e, m[3], b[3], bad, bit0 << 3);
     return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
 }
 
@@ -201,7 +207,7 @@ __device__ __forceinline__ uint32_t requant_word(const int32_t (&acc)[4], int oc
         m[j] = p.x, b[j] = __float_as_int(p.y);
     }
     uint32_t bad = 0;
-    uint32_t w = requant_fast4<U8>(acc, e, m, b, bad, 1u);
+    uint32_t w = (!U8 && e.fuse_bias) ? requant_fast4<U8, true>(acc, e, m, b, bad, 1u) : requant_fast4<U8, false>(acc, e, m, b, bad, 1u);
     if (U8)
     {
         // pad lanes of uint8 tensors must hold 0 (not the zero point): mask them

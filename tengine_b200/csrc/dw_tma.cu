@@ -103,7 +103,16 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     uint32_t bad = 0;
     uint32_t w[TW];
 #pragma unroll
-    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    if (e.fuse_bias)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t));
+    }
+    else
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    }
     if (bad)
     {
 #pragma unroll
@@ -231,7 +240,16 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     uint32_t bad = 0;
     uint32_t w[TW];
 #pragma unroll
-    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    if (e.fuse_bias)
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t));
+    }
+    else
+    {
+#pragma unroll
+        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    }
     if (bad)
     {
 #pragma unroll

@@ -346,6 +346,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
     // ---- validate layers, decide kernels, size the weight arena ----
     std::vector<int> kind(num_layers, -1);
     std::vector<WeightBlob> blobs(num_layers);
+    std::vector<int> fuse_bias(num_layers, 0);
     size_t wtotal = 0;
     const bool no_tc = (flags & TB200_PRERUN_NO_TENSORCORE) != 0;
     for (int li = 0; li < num_layers; li++)
@@ -462,6 +463,24 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         g->out_nchw_dev.push_back(p);
     }
 
+    // ---- per layer: may the fast epilogue fold the bias add into its FMA?  (common.cuh requant_fast_bits<.., FUSE>)
+    //      Decided from the descriptors alone so that every rank of a sharded job reaches the same arena format. ----
+    for (int li = 0; li < num_layers; li++)
+    {
+        const tb200_layer_desc& L = layers[li];
+        if (L.op != TB200_OP_CONV) continue;
+        const TensorInfo& tin = g->tensors[L.inputs[0]];
+        const TensorInfo& tout = g->tensors[L.output];
+        if (tin.d.data_type == TB200_DT_UINT8 || getenv("TB200_NO_FUSE_BIAS")) continue;
+        bool fuse = true;
+        for (int o = 0; o < tout.d.dims[1]; o++)
+        {
+            const double bm = (double)(L.bias ? L.bias[o] : 0) * (double)tin.d.scale * (double)L.weight_scales[o] / (double)tout.d.scale;
+            if (!(bm >= -100.0 && bm <= 100.0)) fuse = false;
+        }
+        fuse_bias[li] = fuse ? 1 : 0;
+    }
+
     // ---- pack weights into a host image of the arena, one H2D copy ----
     if (!(flags & TB200_PRERUN_NO_WEIGHTS))
     {
@@ -534,6 +553,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             float* sc = (float*)(img.data() + blobs[li].scale_off);
             float* fm = (float*)(img.data() + blobs[li].fast_off); // float2 per channel: (multiplier | bias term, bias bits)
             const bool fc = L.op == TB200_OP_FC;
+            const bool fuse = fuse_bias[li] != 0;
             for (int o = 0; o < tout.cp; o++)
             {
                 b[o] = (L.bias && o < OC) ? L.bias[o] : 0;
@@ -557,7 +577,8 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     if (o >= OC) fm[2 * o] = 0.f;
                     else if (fc) fm[2 * o] = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
                     else fm[2 * o] = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
-                    memcpy(&fm[2 * o + 1], &b[o], 4);
+                    if (fuse) fm[2 * o + 1] = (o >= OC) ? 0.f : (float)((double)b[o] * (double)fm[2 * o]); // fl(bias*M)
+                    else memcpy(&fm[2 * o + 1], &b[o], 4);
                 }
             }
         }
@@ -614,6 +635,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 s.epi.w_scale = (const float*)(g->w_arena + blobs[li].scale_off);
                 s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
                 s.btab = (const int32_t*)(g->w_arena + blobs[li].btab_off);
+                s.epi.fuse_bias = fuse_bias[li];
                 ConvShape& cs = s.cs;
                 cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
                 if (fc)

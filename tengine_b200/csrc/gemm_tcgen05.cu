@@ -117,6 +117,7 @@ struct __align__(16) GemmSmemCtl
 __device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // 16 accumulator columns of one row -> 16 output bytes staged in shared memory
+template <bool FUSE>
 __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, uint8_t* gdst, int oc0, int oc_limit,
                                               const EpiParams& e)
 {
@@ -132,7 +133,7 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t 
             const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
             const int32_t b4[4] = {__float_as_int(p01.y), __float_as_int(p01.w), __float_as_int(p23.y), __float_as_int(p23.w)};
             const int32_t a4[4] = {(int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3]};
-            w[j] = requant_fast4<false>(a4, e, m4, b4, bad, 1u << (4 * j));
+            w[j] = FUSE ? requant_fast4<false, true>(a4, e, m4, b4, bad, 1u << (4 * j)) : requant_fast4<false, false>(a4, e, m4, b4, bad, 1u << (4 * j));
         }
         if (bad)
         {
@@ -401,70 +402,53 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tcgen05_fence_after();
             quarter_bar_sync(1 + q); // A: constants visible; the group finished copying the previous stage out
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-            const int units = mtc * nch;
+            // this warp's units: u = sub, sub+4, ... ; unit u = (m-tile i = u / nch, chunk ci = u % nch), tracked incrementally
             uint32_t va[16], vb[16];
-            int u = sub;
-            auto unit_col = [&](int uu) { const int ii = (int)(((uint32_t)uu * g.nch_rcp) >> 16); return ii * g.bnx + (uu - ii * nch) * 16; };
-            if (u < units) tmem_ld16(tbase + unit_col(u), va);
-            while (u < units)
+            int i = 0, ci = sub;
+            while (ci >= nch) ci -= nch, i++;
+            auto process = [&](const uint32_t (&v)[16], int ii, int cc)
+            {
+                const int c = cc * 16;
+                uint8_t* gdst = nullptr;
+                bool skip = false;
+                if (g.direct_store)
+                {
+                    const long long px = row_pixel(g, mt0 + ii, q * 32 + lane);
+                    skip = px < 0 || n0 + c >= g.ocp;
+                    gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
+                }
+                int32_t sx = 0;
+                if (U8) // warp-collective TMEM load: before any lane-dependent branch
+                {
+                    sx = (int32_t)tmem_ld1(tbase + ii * g.bnx + g.block_n);
+                    tmem_ld_wait();
+                }
+                const uint32_t sdst = ost_s + (uint32_t)((ii * 32 + lane) * opitch + c);
+                if (skip)
+                    ;
+                else if (U8)
+                    epilogue_unit_u8(v, sx, padding_taps(g, mt0 + ii, q * 32 + lane), g, par_s + c * 8, sdst, gdst, n0 + c, e);
+                else if (e.fuse_bias)
+                    epilogue_unit<true>(v, par_s + c * 8, sdst, gdst, n0 + c, g.oc, e);
+                else
+                    epilogue_unit<false>(v, par_s + c * 8, sdst, gdst, n0 + c, g.oc, e);
+            };
+            if (i < mtc) tmem_ld16(tbase + i * g.bnx + ci * 16, va);
+            while (i < mtc)
             {
                 tmem_ld_wait();
-                int un = u + 4;
-                if (un < units) tmem_ld16(tbase + unit_col(un), vb);
-                {
-                    const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
-                    uint8_t* gdst = nullptr;
-                    bool skip = false;
-                    if (g.direct_store)
-                    {
-                        const long long px = row_pixel(g, mt0 + i, q * 32 + lane);
-                        skip = px < 0 || n0 + c >= g.ocp;
-                        gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
-                    }
-                    int32_t sx = 0;
-                    if (U8) // warp-collective TMEM load: before any lane-dependent branch
-                    {
-                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
-                        tmem_ld_wait();
-                    }
-                    if (skip)
-                        ;
-                    else if (!U8)
-                        epilogue_unit(va, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
-                    else
-                        epilogue_unit_u8(va, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
-                                         ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, e);
-                }
-                u = un;
-                if (u >= units) break;
+                int i2 = i, c2 = ci + 4;
+                while (c2 >= nch) c2 -= nch, i2++;
+                if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + c2 * 16, vb); // next unit's accumulators are in flight ...
+                process(va, i, ci);                                          // ... while this unit is requantised
+                i = i2, ci = c2;
+                if (i >= mtc) break;
                 tmem_ld_wait();
-                un = u + 4;
-                if (un < units) tmem_ld16(tbase + unit_col(un), va);
-                {
-                    const int i = (int)(((uint32_t)u * g.nch_rcp) >> 16), c = (u - i * nch) * 16;
-                    uint8_t* gdst = nullptr;
-                    bool skip = false;
-                    if (g.direct_store)
-                    {
-                        const long long px = row_pixel(g, mt0 + i, q * 32 + lane);
-                        skip = px < 0 || n0 + c >= g.ocp;
-                        gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
-                    }
-                    int32_t sx = 0;
-                    if (U8) // warp-collective TMEM load: before any lane-dependent branch
-                    {
-                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
-                        tmem_ld_wait();
-                    }
-                    if (skip)
-                        ;
-                    else if (!U8)
-                        epilogue_unit(vb, par_s + c * 8, ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, g.oc, e);
-                    else
-                        epilogue_unit_u8(vb, sx, padding_taps(g, mt0 + i, q * 32 + lane), g, par_s + c * 8,
-                                         ost_s + (uint32_t)((i * 32 + lane) * opitch + c), gdst, n0 + c, e);
-                }
-                u = un;
+                i2 = i, c2 = ci + 4;
+                while (c2 >= nch) c2 -= nch, i2++;
+                if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + c2 * 16, va);
+                process(vb, i, ci);
+                i = i2, ci = c2;
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
     uint32_t bad = 0;
     uint32_t w[TW];
 #pragma unroll
-    for (int t = 0; t < TW; t++) w[t] = requant_fast4<false>(acc[t], e, m, b, bad, 1u << (4 * t));
+    for (int t = 0; t < TW; t++) w[t] = e.fuse_bias ? requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t)) : requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
     if (bad)
     {
 #pragma unroll 1
