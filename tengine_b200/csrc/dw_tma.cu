@@ -18,6 +18,53 @@ namespace tb200 {
 static constexpr int DW_THREADS = 128;
 static constexpr int DW_CH = 32; // channels per CTA (8 words)
 
+// Fused epilogue of both kernels: TW pixels x 4 channels per thread.  The accumulators were initialised with
+// TB200_MAGIC_BITS (|sum of 9 products| < 2^22), so the int->float conversion is a packed FADD on the FMA pipe
+// (common.cuh requant_pair_i8<.., MAGIC_ACC>): the ALU pipe, which also carries this kernel's PRMTs, is the busy one.
+template <int TW>
+__device__ __forceinline__ void dw_epilogue(int (&acc)[TW][4], const FastPar4& f, int c4, int ow0, uint8_t* orow, const ConvShape& s,
+                                            const EpiParams& e)
+{
+    uint32_t w[TW];
+    if (!e.fast_ok || !e.fuse_bias)
+    {
+        // exact path, or a bias too large to fold into the FMA: true accumulators, generic per-word routine
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+        {
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[t][j] -= TB200_MAGIC_BITS;
+            w[t] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
+        }
+    }
+    else
+    {
+        bool gd[TW], any = false;
+#pragma unroll
+        for (int t = 0; t < TW; t++)
+        {
+            w[t] = requant_fast4_i8<true, true>(acc[t], e, f, gd[t]);
+            any |= gd[t];
+        }
+        if (e.q_byte_add)
+        {
+#pragma unroll
+            for (int t = 0; t < TW; t++) w[t] = requant_byte_fix(w[t], e);
+        }
+        if (any)
+        {
+#pragma unroll
+            for (int t = 0; t < TW; t++)
+                if (gd[t])
+                    w[t] = requant_fix_word<true>(w[t], acc[t][0] - TB200_MAGIC_BITS, acc[t][1] - TB200_MAGIC_BITS, acc[t][2] - TB200_MAGIC_BITS,
+                                                  acc[t][3] - TB200_MAGIC_BITS, c4 * 4, e);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+}
+
 template <int TW, int S>
 __global__ void __launch_bounds__(DW_THREADS, 6)
     conv_dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out,
@@ -49,8 +96,8 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     // weights / epilogue constants while the tile is in flight
     const bool active = (r < rows_per_cta) && (oh < s.oh) && (ow0 < s.ow) && (c4 * 4 < s.cp);
     int wj[9][4];
-    float m[4];
-    int32_t b[4];
+    FastPar4 fp;
+    fp.a = fp.b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active)
     {
 #pragma unroll
@@ -60,12 +107,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
 #pragma unroll
             for (int j = 0; j < 4; j++) wj[t][j] = (int)(wv & (0xffu << (8 * j)));
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-        {
-            const float2 p = e.fast_ok ? __ldg(e.fast_par + c4 * 4 + j) : make_float2(0.f, 0.f);
-            m[j] = p.x, b[j] = __float_as_int(p.y);
-        }
+        if (e.fast_ok) fp = fast_par4_ldg(e, c4 * 4);
     }
     mbar_wait(&bar, 0);
     if (!active) return;
@@ -74,7 +116,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
 #pragma unroll
     for (int t = 0; t < TW; t++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[t][j] = 0;
+        for (int j = 0; j < 4; j++) acc[t][j] = TB200_MAGIC_BITS;
     constexpr int COLS = (TW - 1) * S + 3;
     const uint32_t base = smem_u32(dw_smem) + (uint32_t)(((r * S) * tile_cols + ow0 * S) * DW_CH + word * 4);
 #pragma unroll
@@ -93,37 +135,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     }
 
     uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
-    if (!e.fast_ok)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++)
-            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
-        return;
-    }
-    uint32_t bad = 0;
-    uint32_t w[TW];
-#pragma unroll
-    if (e.fuse_bias)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t));
-    }
-    else
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
-    }
-    if (bad)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((bad >> (t * 4 + j)) & 1u) w[t] = requant_fix_byte(w[t], j, acc[t][j], c4 * 4 + j, e);
-    }
-#pragma unroll
-    for (int t = 0; t < TW; t++)
-        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+    dw_epilogue<TW>(acc, fp, c4, ow0, orow, s, e);
 }
 
 // ---- stride-1 variant with three taps per dp4a ---------------------------------------------------------------
@@ -168,8 +180,8 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     }
     const bool active = (r < rows_per_cta) && (oh < s.oh) && (ow0 < s.ow) && (c4 * 4 < s.cp);
     unsigned wr[3][4]; // per filter row and channel: [w(kh,0), w(kh,1), w(kh,2), 0]
-    float m[4];
-    int32_t b[4];
+    FastPar4 fp;
+    fp.a = fp.b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active)
     {
 #pragma unroll
@@ -183,12 +195,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
 #pragma unroll
             for (int j = 0; j < 4; j++) wr[kh][j] = tr[j];
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-        {
-            const float2 p = e.fast_ok ? __ldg(e.fast_par + c4 * 4 + j) : make_float2(0.f, 0.f);
-            m[j] = p.x, b[j] = __float_as_int(p.y);
-        }
+        if (e.fast_ok) fp = fast_par4_ldg(e, c4 * 4);
     }
     mbar_wait(&bar, 0);
     if (!active) return;
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
 #pragma unroll
     for (int t = 0; t < TW; t++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[t][j] = 0;
+        for (int j = 0; j < 4; j++) acc[t][j] = TB200_MAGIC_BITS;
     const uint32_t base = smem_u32(dw_smem) + (uint32_t)((r * tile_cols + ow0) * DW_CH + word * 4);
 #pragma unroll
     for (int kh = 0; kh < 3; kh++)
@@ -230,37 +237,7 @@ __global__ void __launch_bounds__(DW_THREADS, 6)
     }
 
     uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
-    if (!e.fast_ok)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++)
-            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
-        return;
-    }
-    uint32_t bad = 0;
-    uint32_t w[TW];
-#pragma unroll
-    if (e.fuse_bias)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t));
-    }
-    else
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++) w[t] = requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
-    }
-    if (bad)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((bad >> (t * 4 + j)) & 1u) w[t] = requant_fix_byte(w[t], j, acc[t][j], c4 * 4 + j, e);
-    }
-#pragma unroll
-    for (int t = 0; t < TW; t++)
-        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+    dw_epilogue<TW>(acc, fp, c4, ow0, orow, s, e);
 }
 
 // Plan: tile geometry + the 4-D tensor map (C, W, H, N) of the input.  Returns 0, or <0 when this layer must use the

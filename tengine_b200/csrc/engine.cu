@@ -240,6 +240,12 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
         if (flo > -inf) e.fast_lo = fmaxf(-127.f, flo / so); // fl(x / s_out): the same rounded quotient the reference forms
         if (fhi < inf) e.fast_hi = fminf(127.f, fhi / so);
         e.fast_r = 0.f;
+        // integer-domain clamp (common.cuh requant_fast4_i8): [q_lo, q_hi] = what the reference's roundf gives for the
+        // clipped bounds; q' = max(min(q - q_lo, q_hi - q_lo), 0), bytes = q' + q_lo
+        const int q_lo = (int)roundf(e.fast_lo), q_hi = (int)roundf(e.fast_hi);
+        const uint32_t add = (uint32_t)(-q_lo) & 0xffffu, mx = (uint32_t)(q_hi - q_lo) & 0xffffu;
+        e.q_add2 = add | (add << 16), e.q_max2 = mx | (mx << 16);
+        e.q_byte_add = ((uint32_t)q_lo & 0xffu) * 0x01010101u;
     }
     e.fast_ok = (so > 1e-30f && so < 1e30f && tin.scale > 1e-30f && tin.scale < 1e30f) ? 1 : 0;
     return e;
@@ -270,7 +276,7 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
         break;
     case K_CONV_DIRECT: err = launch_conv_direct(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_GEMM:
-    case K_IGEMM: err = launch_gemm_i8(s.gemm, s.out, s.epi, s.btab, g->ctx->num_sms, st); break;
+    case K_IGEMM: err = launch_gemm_i8(s.gemm, s.epi, s.btab, g->ctx->num_sms, st); break;
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
     case K_POINTWISE: err = launch_pointwise(s.in, s.in2, s.out, s.bytes, s.pp, s.u8, st); break;
     case K_CONCAT_PART:
@@ -480,6 +486,29 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         }
         fuse_bias[li] = fuse ? 1 : 0;
     }
+    // ---- int8 fast epilogue rounds BEFORE it clamps (integer-domain clamp on 16-bit lanes, common.cuh): prove from the
+    //      weights that no reachable accumulator can leave the 16-bit range after scaling, else use the exact path ----
+    std::vector<int> fast_int_ok(num_layers, 1);
+    for (int li = 0; li < num_layers; li++)
+    {
+        const tb200_layer_desc& L = layers[li];
+        if (L.op != TB200_OP_CONV && L.op != TB200_OP_FC) continue;
+        const TensorInfo& tin = g->tensors[L.inputs[0]];
+        const TensorInfo& tout = g->tensors[L.output];
+        if (tin.d.data_type == TB200_DT_UINT8) continue;
+        const int OC = tout.d.dims[1];
+        const size_t kk = L.op == TB200_OP_FC ? (size_t)tin.d.dims[1] * tin.d.dims[2] * tin.d.dims[3]
+                                              : (size_t)(tin.d.dims[1] / L.group) * L.kernel_h * L.kernel_w;
+        const int8_t* wsrc = (const int8_t*)L.weight;
+        for (int o = 0; o < OC; o++)
+        {
+            double sumabs = 0;
+            for (size_t k = 0; k < kk; k++) sumabs += abs((int)wsrc[(size_t)o * kk + k]);
+            const double M = (double)tin.d.scale * (double)L.weight_scales[o] / (double)tout.d.scale;
+            const double bound = (128.0 * sumabs + fabs((double)(L.bias ? L.bias[o] : 0))) * fabs(M);
+            if (!(bound < 32000.0)) fast_int_ok[li] = 0;
+        }
+    }
 
     // ---- pack weights into a host image of the arena, one H2D copy ----
     if (!(flags & TB200_PRERUN_NO_WEIGHTS))
@@ -574,11 +603,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 }
                 else
                 {
-                    if (o >= OC) fm[2 * o] = 0.f;
-                    else if (fc) fm[2 * o] = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
-                    else fm[2 * o] = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
-                    if (fuse) fm[2 * o + 1] = (o >= OC) ? 0.f : (float)((double)b[o] * (double)fm[2 * o]); // fl(bias*M)
-                    else memcpy(&fm[2 * o + 1], &b[o], 4);
+                    // channel pairs interleaved (common.cuh FastPar4): { M[2k], M[2k+1], y[2k], y[2k+1] }
+                    float* fmM = fm + (size_t)(o >> 1) * 4 + (o & 1);
+                    float* fmY = fmM + 2;
+                    if (o >= OC) *fmM = 0.f;
+                    else if (fc) *fmM = (tin.d.scale * sc[o]) / tout.d.scale; // fc_ref.c:225, the reference's own requant scale
+                    else *fmM = (float)((double)tin.d.scale * (double)sc[o] / (double)tout.d.scale);
+                    if (fuse) *fmY = (o >= OC) ? 0.f : (float)((double)b[o] * (double)*fmM); // fl(bias*M)
+                    else memcpy(fmY, &b[o], 4);
                 }
             }
         }
@@ -636,6 +668,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
                 s.btab = (const int32_t*)(g->w_arena + blobs[li].btab_off);
                 s.epi.fuse_bias = fuse_bias[li];
+                if (!u8 && !fast_int_ok[li]) s.epi.fast_ok = 0;
                 ConvShape& cs = s.cs;
                 cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
                 if (fc)
@@ -664,14 +697,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)
                 {
-                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.cs, u8 ? 1 : 0);
+                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.out, s.cs, u8 ? 1 : 0);
                     if (rc) return bail(fail(rc, "layer %d: implicit-GEMM plan failed", li));
                 }
                 if (s.kind == K_GEMM)
                 {
                     const long long m = fc ? N : (long long)N * H * W;
                     const int kdim = fc ? H * W * tin.cp : tin.cp;
-                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 : 0);
+                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, s.out, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 : 0);
                     if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
                 }
             }
@@ -1009,10 +1042,10 @@ int tb200k_gemm_i8(const void* in, const void* weight, void* out, int64_t m, int
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(TB200_ERR_NO_DEVICE, "no CUDA device");
     GemmPlan plan;
-    int rc = gemm_plan_create(&plan, in, k_pad, weight, m, k_pad, oc, cpad(oc), cpad(oc), 0, 0);
+    int rc = gemm_plan_create(&plan, in, k_pad, weight, out, m, k_pad, oc, cpad(oc), cpad(oc), 0, 0);
     if (rc) return fail(rc, "gemm plan failed");
     EpiParams p = epi_from_abi(e);
-    K_LAUNCH(launch_gemm_i8(plan, out, p, nullptr, sms, (cudaStream_t)stream));
+    K_LAUNCH(launch_gemm_i8(plan, p, nullptr, sms, (cudaStream_t)stream));
 }
 int tb200k_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, void* stream)
 {

@@ -11,11 +11,14 @@
 //   warp 0    : TMA producer  (cp.async.bulk.tensor.2d -> 128B/64B/32B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1    : MMA issuer    (one elected lane: tcgen05.mma.cta_group::1.kind::i8, 128 x BN x 32 per instruction;
 //                              tcgen05.commit releases smem stages / publishes the accumulator)
-//   warps 2-17: epilogue      (four warps per TMEM lane quarter, 16-column chunks dealt round-robin: tcgen05.ld 32x32b ->
-//                              registers -> requant_fast4 -> int8 -> padded smem tile -> coalesced 16-byte global stores)
+//   warps 2-17: epilogue      (four warps per TMEM lane quarter; a warp owns whole "store groups" = 32 rows x 16/32/64
+//                              channels: tcgen05.ld 32x32b -> registers -> requant_fast4_i8 -> bytes -> its own swizzled
+//                              smem buffer -> ONE TMA store per group (cp.async.bulk.tensor, double-buffered).  No
+//                              barrier between epilogue warps, no address arithmetic for the stores, rows outside
+//                              the tensor are clipped by the TMA unit.)
 // Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
-// These layers are HBM-bound (K is 32..1024): the budget is ~8-10 issued instructions per output element, which is
-// why the epilogue uses the ~10-instruction requant_fast (common.cuh) and keeps per-channel constants in smem.
+// K is small (32..1024), so these layers are bound by the epilogue's ALU-pipe issue rate, not by the tensor pipe:
+// see common.cuh (requant_fast4_i8) for the instruction budget.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,7 +33,7 @@ static constexpr int BLOCK_M = 128;
 static constexpr int EPI_WARPS = 16; // four per TMEM lane quarter
 static constexpr int EPI_THREADS = EPI_WARPS * 32;
 static constexpr int GEMM_THREADS = 64 + EPI_THREADS;
-static constexpr int OUT_PAD = 16; // row padding of the staged output tile (bank-conflict-free 16-byte accesses)
+static constexpr int PAR_MAX = 2048; // channels whose epilogue constants stay resident in smem for the whole kernel
 static constexpr int MAX_STAGES = 8;
 
 // K-major operand tile in shared memory, rows of `swizzle` bytes, 8-row groups `8*swizzle` bytes apart
@@ -62,12 +65,11 @@ __host__ __device__ inline uint32_t make_idesc_i8(int block_n, bool a_signed, bo
 
 struct GemmArgs
 {
-    long long m;
     int m_tiles, num_super; // 32-bit on purpose: 64-bit divisions in the tile decode cost ~100 instructions each
     int k_blocks, n_tiles, block_n, block_k, stages, swizzle;
     int mt;     // m-tiles (128 rows each) per accumulator stage
-    uint32_t nch_rcp, bw_rcp, bh_rcp; // ceil(65536/d): q = (x * rcp) >> 16 is exact for x < 4096, d <= 256
-    int oc, ocp, ldo;
+    uint32_t bw_rcp, bh_rcp; // ceil(65536/d): q = (x * rcp) >> 16 is exact for x < 4096, d <= 256
+    int oc, ocp;
     uint32_t idesc;
     uint32_t tmem_cols;
     // conv mode (implicit GEMM): an m-tile is a bw x bh x bn patch of output pixels, a k-block is (tap, channel block)
@@ -76,7 +78,11 @@ struct GemmArgs
     uint32_t a_tx_bytes; // bytes one A load delivers (block_k * rows of the patch)
     // uint8: the B tile carries 16 extra rows, row block_n = all ones, so accumulator column block_n = sum_k x (per pixel)
     int u8, bnx, taps, in_h, in_w;
-    int direct_store; // 1: each lane writes its 16 output bytes straight to global memory (no smem staging / copy-out)
+    // epilogue / stores
+    int cs, ngroups; // 16-column chunks per store group (1, 2 or 4) and groups per m-tile
+    int rows_valid;  // rows of an m-tile that are output pixels (128, or bw*bh*bn of a smaller conv patch)
+    int out_mode;    // coordinates of the output map: 0 (c, row, 0)  1 (c, pixel in image, image)  2 (c, x, image row)
+    int par_all;     // the constants of every channel are resident (loaded once); else reloaded per N tile
     const int32_t* btab; // [taps][OCp]: zx * (sum_c w[oc][tap][c] - Cin*zw), the correction a padding tap needs
 };
 
@@ -90,22 +96,6 @@ __device__ __forceinline__ void tile_origin(const GemmArgs& g, int mt, int& n0, 
     n0 = nn * g.bn;
 }
 
-// row r of m-tile mt -> linear output pixel index, or -1 when the row is padding of the tile
-__device__ __forceinline__ long long row_pixel(const GemmArgs& g, int mt, int r)
-{
-    if (!g.conv)
-    {
-        const long long px = (long long)mt * BLOCK_M + r;
-        return px < g.m ? px : -1;
-    }
-    int n0, oh0, ow0;
-    tile_origin(g, mt, n0, oh0, ow0);
-    const int t = (int)(((uint32_t)r * g.bw_rcp) >> 16), w = r - t * g.bw;
-    const int n = (int)(((uint32_t)t * g.bh_rcp) >> 16), h = t - n * g.bh;
-    if (n >= g.bn || n0 + n >= g.nimg || oh0 + h >= g.oh || ow0 + w >= g.ow) return -1;
-    return ((long long)(n0 + n) * g.oh + oh0 + h) * g.ow + ow0 + w;
-}
-
 struct __align__(16) GemmSmemCtl
 {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES];
@@ -114,54 +104,59 @@ struct __align__(16) GemmSmemCtl
     uint32_t pad[3];
 };
 
-__device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
-// 16 accumulator columns of one row -> 16 output bytes staged in shared memory
+// 16 accumulator columns of one row -> 16 output bytes into the warp's staging buffer (int8, fast path).
 template <bool FUSE>
-__device__ __forceinline__ void epilogue_unit(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, uint8_t* gdst, int oc0, int oc_limit,
-                                              const EpiParams& e)
+__device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, int oc0, const EpiParams& e)
 {
     uint32_t w[4];
-    if (e.fast_ok)
+    float gw[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
     {
-        uint32_t bad = 0;
+        float4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = lds_f4(par_addr + h * 64 + k * 16);
+        const int32_t a8[8] = {(int32_t)v[h * 8], (int32_t)v[h * 8 + 1], (int32_t)v[h * 8 + 2], (int32_t)v[h * 8 + 3],
+                               (int32_t)v[h * 8 + 4], (int32_t)v[h * 8 + 5], (int32_t)v[h * 8 + 6], (int32_t)v[h * 8 + 7]};
+        requant_fast8_i8<FUSE>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
+    }
+    if (e.q_byte_add)
+    {
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
+    }
+    if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
+    {
+        // rare (2.4e-4 of the elements): exact recomputation of the guarded bytes
 #pragma unroll
         for (int j = 0; j < 4; j++)
-        {
-            const float4 p01 = lds_f4(par_addr + j * 32);
-            const float4 p23 = lds_f4(par_addr + j * 32 + 16);
-            const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
-            const int32_t b4[4] = {__float_as_int(p01.y), __float_as_int(p01.w), __float_as_int(p23.y), __float_as_int(p23.w)};
-            const int32_t a4[4] = {(int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3]};
-            w[j] = FUSE ? requant_fast4<false, true>(a4, e, m4, b4, bad, 1u << (4 * j)) : requant_fast4<false, false>(a4, e, m4, b4, bad, 1u << (4 * j));
-        }
-        if (bad)
-        {
-            // rare (2.4e-4 of the elements): exact recomputation; fully unrolled so v[] stays in registers
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, (int32_t)v[k], oc0 + k, e);
-        }
+            if (gw[j] > 0.5f - TB200_TIE_EPS)
+                w[j] = requant_fix_word<FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, e);
     }
-    else
+    sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+}
+
+// degenerate scales / accumulators that could leave the 16-bit clamp range: literal arithmetic for every element
+__device__ __forceinline__ void epilogue_unit_exact(const uint32_t (&v)[16], uint32_t dst_addr, int oc0, int oc_limit, const EpiParams& e)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
     {
-        // degenerate scales: literal arithmetic for every element
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-        {
-            if ((k & 3) == 0) w[k >> 2] = 0;
-            if (oc0 + k < oc_limit) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], oc0 + k, e) & 0xffu) << (8 * (k & 3));
-        }
+        if ((k & 3) == 0) w[k >> 2] = 0;
+        if (oc0 + k < oc_limit) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], oc0 + k, e) & 0xffu) << (8 * (k & 3));
     }
-    if (gdst) *reinterpret_cast<uint4*>(gdst) = make_uint4(w[0], w[1], w[2], w[3]);
-    else sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+    sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
 
 // uint8 flavour: v = sum x*w over in-bounds taps (raw bytes), sx = sum x.  The true accumulator is
 //   sum (x-zx)(w-zw) = v - zw*sx + corr[oc] + sum_{padding taps t} btab[t][oc]
 // with corr[oc] = -zx*sum_k w + taps*Cin*zx*zw (interior pixels) folded into the per-channel constants.
+template <bool EXACT>
 __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_t sx, uint64_t pad_mask, const GemmArgs& g, uint32_t par_addr,
-                                                 uint32_t dst_addr, uint8_t* gdst, int oc0, const EpiParams& e)
+                                                 uint32_t dst_addr, int oc0, const EpiParams& e)
 {
     const int32_t rowc = -e.w_zero * sx;
     int32_t a[16];
@@ -180,7 +175,7 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
             }
     }
     uint32_t w[4];
-    if (e.fast_ok)
+    if (!EXACT)
     {
         uint32_t bad = 0;
 #pragma unroll
@@ -189,12 +184,11 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
             const float4 p01 = lds_f4(par_addr + j * 32);
             const float4 p23 = lds_f4(par_addr + j * 32 + 16);
             const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
-            const int32_t z4[4] = {0, 0, 0, 0};
             // corr[oc] travels in the .y lanes
             a[j * 4 + 0] += __float_as_int(p01.y), a[j * 4 + 1] += __float_as_int(p01.w);
             a[j * 4 + 2] += __float_as_int(p23.y), a[j * 4 + 3] += __float_as_int(p23.w);
             const int32_t a4[4] = {a[j * 4], a[j * 4 + 1], a[j * 4 + 2], a[j * 4 + 3]};
-            w[j] = requant_fast4<true>(a4, e, m4, z4, bad, 1u << (4 * j));
+            w[j] = requant_fast4_u8(a4, e, m4, bad, 1u << (4 * j));
         }
         // pad lanes of uint8 tensors hold 0, not the zero point
 #pragma unroll
@@ -221,8 +215,7 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
             }
         }
     }
-    if (gdst) *reinterpret_cast<uint4*>(gdst) = make_uint4(w[0], w[1], w[2], w[3]);
-    else sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
+    sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
 
 // taps of output pixel (oh, ow) that fall outside the image (bit t = kh*kw_n + kw)
@@ -243,21 +236,25 @@ __device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int 
     return m;
 }
 
-template <bool U8>
+// MODE: 0 fast epilogue, 1 fast epilogue with the bias folded into the FMA (int8 only), 2 exact epilogue.
+// CS: 16-column chunks per store group (1, 2 or 4).  Compile-time so that each kernel carries exactly one epilogue body.
+template <bool U8, int MODE, int CS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                           uint8_t* __restrict__ out, const GemmArgs g, const __grid_constant__ EpiParams e)
+                           const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out_tail,
+                           const GemmArgs g, const __grid_constant__ EpiParams e)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // operand ring first (1024-byte aligned for the 128B swizzle), then the control block, the per-quarter epilogue
-    // constants and the per-quarter output staging tiles
+    // operand ring first (1024-byte aligned for the 128B swizzle), then the per-warp output staging buffers (1024-byte
+    // aligned: their TMA swizzle pattern is a function of the address), the control block and the epilogue constants
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.bnx * g.block_k;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-    GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(smem + (size_t)g.stages * stage_bytes);
-    const int opitch = g.block_n + OUT_PAD;
-    const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl);   // 4 x [block_n] float2 (m, bias)
-    const uint32_t ost_base = par_base + 4u * (uint32_t)g.block_n * 8u;           // 4 x [mt*32][block_n + OUT_PAD]
+    constexpr uint32_t buf_bytes = 512u * CS; // 32 rows x 16*CS bytes
+    uint8_t* stg = smem + (size_t)g.stages * stage_bytes;
+    const uint32_t stg_base = smem_u32(stg);
+    GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(stg + (size_t)EPI_WARPS * 2 * buf_bytes);
+    const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl); // [par channels] x 8 bytes (see FastPar4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int acc_cols = g.mt * g.bnx; // TMEM columns of one accumulator stage
@@ -369,18 +366,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     {
         // ===================== epilogue (warps 2..17) =====================
         // TMEM lane quarter q (hardware rule: a warp may only touch lanes 32*(warp_id % 4)...) is served by the four
-        // warps {q, q+4, q+8, q+12}: they deal the (m-tile, 16-column chunk) units of the stage round-robin, stage the
-        // requantised bytes of "their" rows in smem and copy them out with coalesced 16-byte stores.  Only these 128
-        // threads synchronise with each other (named barriers); nothing here is block-wide.
+        // warps {q, q+4, q+8, q+12}.  The work of an accumulator stage is cut into store groups (m-tile i, columns
+        // [grp*16*cs, (grp+1)*16*cs)) of 32 rows each, dealt round-robin to the quarter's warps.  A warp requantises
+        // its group chunk by chunk (16 columns per tcgen05.ld, the next chunk's load in flight), writes the bytes to
+        // its own swizzled staging buffer and hands the buffer to the TMA unit with one store.
         const int q = warp & 3;
         const int sub = (warp - 2) >> 2;
-        const int tq = sub * 32 + lane; // 0..127 inside the quarter group
-        const int nch = g.block_n >> 4; // 16-column chunks per m-tile
-        const uint32_t par_s = par_base + (uint32_t)(q * g.block_n * 8);
-        const uint32_t ost_s = ost_base + (uint32_t)(q * g.mt * 32 * opitch);
+        const int ngroups = g.ngroups;
+        int qrows = g.rows_valid - q * 32; // rows of this quarter that are output pixels
+        qrows = qrows < 0 ? 0 : (qrows > 32 ? 32 : qrows);
+        const CUtensorMap* tm_out = (qrows == 32) ? &tmap_out : &tmap_out_tail;
+        const uint32_t buf0 = stg_base + (uint32_t)(warp - 2) * 2u * buf_bytes;
+        // swizzle of the staging buffer = the output map's swizzle: 16-byte chunk index ^= row bits (Swizzle<1|2,4,3>)
+        const uint32_t xl = CS == 4 ? (uint32_t)((lane >> 1) & 3) << 4 : (CS == 2 ? (uint32_t)((lane >> 2) & 1) << 4 : 0u);
+        const uint32_t row_off = (uint32_t)lane * 16u * CS;
+        uint32_t ucount = 0; // groups this warp has stored (buffer parity)
+        const int par_ch = g.n_tiles * g.block_n;
+        const bool fast = MODE != 2;
+        if (g.par_all)
+        {
+            // per-channel fast-path constants of every N tile, once; pad / overhanging channels get (0, 0)
+            for (int c = threadIdx.x - 64; c < par_ch; c += EPI_THREADS)
+                sts_f2(par_base + c * 8, (c < g.ocp && (fast || U8)) ? __ldg(e.fast_par + c) : make_float2(0.f, 0.f));
+            epilogue_bar_sync();
+        }
+        if (lane == 0 && qrows > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm_out)) : "memory");
         int as = 0;
         uint32_t aphase = 0;
-        int loaded_n0 = -1;
         for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
         {
             const int msup = st / g.n_tiles;
@@ -388,85 +400,97 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int n0 = (st - msup * g.n_tiles) * g.block_n;
             const int rem = g.m_tiles - mt0;
             const int mtc = rem < g.mt ? rem : g.mt;
-            if (n0 != loaded_n0)
+            uint32_t par_s = par_base + (uint32_t)n0 * 8u;
+            if (!g.par_all)
             {
-                // per-channel fast-path constants (m, bias) of this N tile; pad / overhanging channels get (0, 0)
-                for (int c = tq; c < g.block_n; c += 128)
-                {
-                    const int oc = n0 + c;
-                    sts_f2(par_s + c * 8, (oc < g.ocp && e.fast_ok) ? __ldg(e.fast_par + oc) : make_float2(0.f, 0.f));
-                }
-                loaded_n0 = n0;
+                epilogue_bar_sync(); // every warp is done with the previous tile's constants
+                for (int c = threadIdx.x - 64; c < g.block_n; c += EPI_THREADS)
+                    sts_f2(par_base + c * 8, (n0 + c < g.ocp && (fast || U8)) ? __ldg(e.fast_par + n0 + c) : make_float2(0.f, 0.f));
+                epilogue_bar_sync();
+                par_s = par_base;
             }
             mbar_wait(&ctl->tmem_full[as], aphase);
             tcgen05_fence_after();
-            quarter_bar_sync(1 + q); // A: constants visible; the group finished copying the previous stage out
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-            // this warp's units: u = sub, sub+4, ... ; unit u = (m-tile i = u / nch, chunk ci = u % nch), tracked incrementally
-            uint32_t va[16], vb[16];
-            int i = 0, ci = sub;
-            while (ci >= nch) ci -= nch, i++;
-            auto process = [&](const uint32_t (&v)[16], int ii, int cc)
+            if (qrows > 0)
             {
-                const int c = cc * 16;
-                uint8_t* gdst = nullptr;
-                bool skip = false;
-                if (g.direct_store)
+                // groups of this warp: flattened index u = i * ngroups + grp, u = sub, sub + 4, ...
+                uint32_t v0[16], v1[16];
+                int i = 0, grp = sub;
+                while (grp >= ngroups) grp -= ngroups, i++;
+                if (CS > 1 && i < mtc) tmem_ld16(tbase + i * g.bnx + grp * (CS * 16), v0);
+                while (i < mtc)
                 {
-                    const long long px = row_pixel(g, mt0 + ii, q * 32 + lane);
-                    skip = px < 0 || n0 + c >= g.ocp;
-                    gdst = out + (size_t)(px < 0 ? 0 : px) * g.ldo + n0 + c;
+                    int i2 = i, g2 = grp + 4; // the group after this one
+                    while (g2 >= ngroups) g2 -= ngroups, i2++;
+                    const uint32_t buf = buf0 + (ucount & 1u) * buf_bytes;
+                    if (lane == 0) bulk_wait_read<1>(); // the store issued two groups ago has finished reading this buffer
+                    __syncwarp();
+                    int32_t sx = 0;
+                    uint64_t pad = 0;
+                    if (U8)
+                    {
+                        // warp-collective TMEM load (column block_n = sum of the pixel's inputs), once per group
+                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
+                        pad = padding_taps(g, mt0 + i, q * 32 + lane);
+                    }
+                    const uint32_t tg = tbase + i * g.bnx + grp * (CS * 16);
+                    const int cg0 = grp * (CS * 16); // first column of the group inside the N tile
+                    const uint32_t sdst = buf + row_off;
+                    auto unit = [&](const uint32_t (&v)[16], int k)
+                    {
+                        const int c = cg0 + k * 16;
+                        const uint32_t dst = sdst + (((uint32_t)k << 4) ^ xl);
+                        if (U8) epilogue_unit_u8<MODE == 2>(v, sx, pad, g, par_s + c * 8, dst, n0 + c, e);
+                        else if (MODE == 2) epilogue_unit_exact(v, dst, n0 + c, g.oc, e);
+                        else epilogue_unit_fast<MODE == 1>(v, par_s + c * 8, dst, n0 + c, e);
+                    };
+                    if (CS == 1)
+                    {
+                        tmem_ld16(tg, v0);
+                        tmem_ld_wait();
+                        unit(v0, 0);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < CS; k++)
+                        {
+                            tmem_ld_wait();
+                            // the next chunk's accumulators are in flight while this one is requantised
+                            if (k + 1 < CS) tmem_ld16(tg + (k + 1) * 16, (k & 1) ? v0 : v1);
+                            else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16), v0);
+                            unit((k & 1) ? v1 : v0, k);
+                        }
+                    }
+                    fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA unit
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        int x1, x2 = 0;
+                        if (!g.conv)
+                            x1 = (mt0 + i) * BLOCK_M;
+                        else
+                        {
+                            int cn0, coh0, cow0;
+                            tile_origin(g, mt0 + i, cn0, coh0, cow0);
+                            if (g.out_mode == 0) x1 = cn0 * g.oh * g.ow;
+                            else if (g.out_mode == 1) x1 = coh0 * g.ow, x2 = cn0;
+                            else x1 = cow0, x2 = cn0 * g.oh + coh0;
+                        }
+                        tma_store_3d(tm_out, buf, n0 + cg0, x1 + q * 32, x2);
+                        bulk_commit();
+                    }
+                    ucount++;
+                    i = i2, grp = g2;
                 }
-                int32_t sx = 0;
-                if (U8) // warp-collective TMEM load: before any lane-dependent branch
-                {
-                    sx = (int32_t)tmem_ld1(tbase + ii * g.bnx + g.block_n);
-                    tmem_ld_wait();
-                }
-                const uint32_t sdst = ost_s + (uint32_t)((ii * 32 + lane) * opitch + c);
-                if (skip)
-                    ;
-                else if (U8)
-                    epilogue_unit_u8(v, sx, padding_taps(g, mt0 + ii, q * 32 + lane), g, par_s + c * 8, sdst, gdst, n0 + c, e);
-                else if (e.fuse_bias)
-                    epilogue_unit<true>(v, par_s + c * 8, sdst, gdst, n0 + c, g.oc, e);
-                else
-                    epilogue_unit<false>(v, par_s + c * 8, sdst, gdst, n0 + c, g.oc, e);
-            };
-            if (i < mtc) tmem_ld16(tbase + i * g.bnx + ci * 16, va);
-            while (i < mtc)
-            {
-                tmem_ld_wait();
-                int i2 = i, c2 = ci + 4;
-                while (c2 >= nch) c2 -= nch, i2++;
-                if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + c2 * 16, vb); // next unit's accumulators are in flight ...
-                process(va, i, ci);                                          // ... while this unit is requantised
-                i = i2, ci = c2;
-                if (i >= mtc) break;
-                tmem_ld_wait();
-                i2 = i, c2 = ci + 4;
-                while (c2 >= nch) c2 -= nch, i2++;
-                if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + c2 * 16, va);
-                process(vb, i, ci);
-                i = i2, ci = c2;
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]); // accumulator drained: the MMA warp may overwrite it
             if (++as == 2) as = 0, aphase ^= 1;
-            if (g.direct_store) continue; // bytes already went to global memory
-            quarter_bar_sync(5 + q); // B: the quarter's staged rows are complete
-            // coalesced copy-out of this quarter's rows: consecutive threads write consecutive 16-byte pieces
-            const int total_vec = mtc * 32 * nch;
-            for (int vi = tq; vi < total_vec; vi += 128)
-            {
-                const int lr = (int)(((uint32_t)vi * g.nch_rcp) >> 16);
-                const int cv = vi - lr * nch;
-                const long long grow = row_pixel(g, mt0 + (lr >> 5), q * 32 + (lr & 31));
-                if (grow >= 0 && n0 + cv * 16 < g.ocp)
-                    *reinterpret_cast<uint4*>(out + (size_t)grow * g.ldo + n0 + cv * 16) = lds_u4(ost_s + (uint32_t)(lr * opitch + cv * 16));
-            }
         }
+        if (lane == 0) bulk_wait<0>(); // all of this warp's stores have completed
     }
 
     tcgen05_fence_before();
@@ -528,7 +552,43 @@ int gemm_block_n(int ocp, int u8)
     return ocp <= 240 ? ocp : 112; // +16 rows for the ones-row keeps the UMMA N at <= 256 / 128
 }
 
-int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
+// Store-group width and output tensor maps.  A group is 32 rows x 16*cs channels; cs is the largest of 4 / 2 / 1 that
+// divides the N tile's chunk count and deals the stage's groups evenly to the four warps of a TMEM lane quarter.
+static int plan_epilogue(GemmPlan* p, const void* out, uint64_t d1, uint64_t d2)
+{
+    const int nch = p->block_n / 16;
+    int cs = 1;
+    for (int c = 4; c >= 1; c >>= 1)
+        if (nch % c == 0 && ((p->mt * (nch / c)) % 4 == 0 || c == 1))
+        {
+            cs = c;
+            break;
+        }
+    if (const char* ev = getenv("TB200_GEMM_STORE_CS"))
+    {
+        const int f = atoi(ev);
+        if ((f == 1 || f == 2 || f == 4) && nch % f == 0) cs = f;
+    }
+    p->cs = cs, p->ngroups = nch / cs;
+    const uint64_t dims[3] = {(uint64_t)p->ocp, d1, d2};
+    const uint64_t strides[2] = {(uint64_t)p->ldo, (uint64_t)p->ldo * d1};
+    const int swz = cs == 4 ? 64 : (cs == 2 ? 32 : 0);
+    const uint32_t box[3] = {(uint32_t)(16 * cs), 32u, 1u};
+    int rc = tmap_encode(p->tmap_out, out, 3, dims, strides, box, nullptr, swz);
+    if (rc) return rc;
+    const int tail = p->rows_valid % 32;
+    const uint32_t box_t[3] = {(uint32_t)(16 * cs), (uint32_t)(tail ? tail : 32), 1u};
+    return tmap_encode(p->tmap_out_tail, out, 3, dims, strides, box_t, nullptr, swz);
+}
+
+// shared memory the epilogue needs next to the operand ring
+static int epilogue_smem_bytes(const GemmPlan* p)
+{
+    const int par_ch = p->n_tiles * p->block_n;
+    return EPI_WARPS * 2 * 512 * 4 /* staging at the widest cs */ + (par_ch <= PAR_MAX ? par_ch : p->block_n) * 8 + (int)sizeof(GemmSmemCtl) + 2048;
+}
+
+int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, void* out, long long m, int k, int oc, int ocp, int ldo,
                      int variant, int u8)
 {
     if (m <= 0 || k <= 0 || (k & 15) || (ocp & 15) || (lda & 15) || (ldo & 15)) return TB200_ERR_INVALID;
@@ -548,20 +608,21 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, l
     p->mt = 1;
     if (p->n_tiles == 1)
         while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
-    const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
-    int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
+    int stages = (224 * 1024 - epilogue_smem_bytes(p)) / (a_bytes + b_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return TB200_ERR_INVALID;
     p->stages = stages;
     int rc = encode_2d(p->tmap_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, p->block_k, BLOCK_M, p->swizzle);
     if (rc) return rc;
     rc = encode_2d(p->tmap_b, b, (uint64_t)k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)k, p->block_k, p->bnx, p->swizzle);
-    return rc;
+    if (rc) return rc;
+    p->rows_valid = BLOCK_M, p->out_mode = 0;
+    return plan_epilogue(p, out, (uint64_t)m, 1);
 }
 
 // Implicit-GEMM plan for a dense (group 1, dilation 1) convolution with any kernel size and stride 1 or 2:
 // A = 4-D tensor map (C, W, H, N) over the NHWC input with traversal strides (1, s, s, 1); B = [OCp][taps*Cp].
-int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const ConvShape& s, int u8)
+int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out, const ConvShape& s, int u8)
 {
     if (s.group != 1 || s.dh != 1 || s.dw != 1 || s.sh != s.sw || (s.sh != 1 && s.sh != 2)) return TB200_ERR_UNSUPPORTED;
     const int taps = s.kh * s.kw;
@@ -602,8 +663,7 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
     p->mt = 1;
     if (p->n_tiles == 1)
         while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
-    const int epi_bytes = 4 * p->block_n * 8 + BLOCK_M * p->mt * (p->block_n + OUT_PAD) + 2048;
-    int stages = (224 * 1024 - epi_bytes) / (a_bytes + b_bytes);
+    int stages = (224 * 1024 - epilogue_smem_bytes(p)) / (a_bytes + b_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return TB200_ERR_INVALID;
     p->stages = stages;
@@ -614,49 +674,81 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, const Conv
     if (box[1] > 256 || box[2] > 256 || box[3] > 256) return TB200_ERR_UNSUPPORTED;
     int rc = tmap_encode(p->tmap_a, in, 4, dims, strides, box, estr, p->swizzle);
     if (rc) return rc;
-    return encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)p->k, p->block_k, p->bnx, p->swizzle);
+    rc = encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)p->k, p->block_k, p->bnx, p->swizzle);
+    if (rc) return rc;
+    // The rows of an m-tile are consecutive output pixels along one axis of the NHWC output (see the patch shapes above):
+    //   bn > 1 (whole images)   : rows = pixels of bn consecutive images        -> map (C, N*OH*OW, 1), clipped at the end
+    //   bn == 1, bw == OW       : rows = pixels of image n from row oh0 on       -> map (C, OH*OW, N), clipped per image
+    //   bw == 128 < OW          : rows = 128 pixels of one image row             -> map (C, OW, N*OH), clipped per row
+    p->rows_valid = p->bw * p->bh * p->bn;
+    if (p->bw != s.ow)
+    {
+        p->out_mode = 2;
+        return plan_epilogue(p, out, (uint64_t)s.ow, (uint64_t)s.n * s.oh);
+    }
+    if (p->bn > 1)
+    {
+        p->out_mode = 0;
+        return plan_epilogue(p, out, (uint64_t)s.n * s.oh * s.ow, 1);
+    }
+    p->out_mode = 1;
+    return plan_epilogue(p, out, (uint64_t)s.oh * s.ow, (uint64_t)s.n);
 }
 
-cudaError_t launch_gemm_i8(const GemmPlan& p, void* out, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st)
+cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st)
 {
-    if (p.block_n <= 0 || p.mt <= 0 || p.stages <= 0) return cudaErrorInvalidValue; // plan was never created
+    if (p.block_n <= 0 || p.mt <= 0 || p.stages <= 0 || p.cs <= 0) return cudaErrorInvalidValue; // plan was never created
     GemmArgs g;
-    g.m = p.m, g.m_tiles = (int)p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
+    g.m_tiles = (int)p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;
     g.conv = p.conv, g.cblocks = p.cblocks, g.kw_n = p.kw_n, g.pad_h = p.pad_h, g.pad_w = p.pad_w, g.cstride = p.cstride, g.cp = p.cp;
     g.bw = p.bw, g.bh = p.bh, g.bn = p.bn, g.tiles_w = p.tiles_w, g.tiles_h = p.tiles_h, g.oh = p.oh, g.ow = p.ow, g.nimg = p.nimg;
     g.a_tx_bytes = p.a_tx_bytes;
     g.u8 = p.u8, g.bnx = p.bnx, g.taps = p.taps, g.in_h = p.in_h, g.in_w = p.in_w, g.btab = btab;
-    static const int direct_env = getenv("TB200_GEMM_DIRECT_STORE") ? atoi(getenv("TB200_GEMM_DIRECT_STORE")) : 0;
-    g.direct_store = direct_env;
     g.mt = p.mt;
     g.num_super = (int)(((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles);
-    g.nch_rcp = (65536u + (uint32_t)(p.block_n >> 4) - 1) / (uint32_t)(p.block_n >> 4);
     g.bw_rcp = p.conv ? (65536u + (uint32_t)p.bw - 1) / (uint32_t)p.bw : 0;
     g.bh_rcp = p.conv ? (65536u + (uint32_t)p.bh - 1) / (uint32_t)p.bh : 0;
-    g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp, g.ldo = p.ldo;
+    g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp;
     g.idesc = make_idesc_i8(p.bnx, !p.u8, !p.u8);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * p.mt * p.bnx)) cols <<= 1;
     g.tmem_cols = cols;
+    g.cs = p.cs, g.ngroups = p.ngroups, g.rows_valid = p.rows_valid, g.out_mode = p.out_mode;
+    const int par_ch = p.n_tiles * p.block_n;
+    g.par_all = par_ch <= PAR_MAX ? 1 : 0;
     const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.bnx * p.block_k + 1023) & ~1023;
-    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + sizeof(GemmSmemCtl) + 4 * (size_t)p.block_n * 8 +
-                        (size_t)BLOCK_M * p.mt * (p.block_n + OUT_PAD) + 1024;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        cudaError_t err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err != cudaSuccess) return err;
-        attr_set = true;
-    }
+    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + (size_t)EPI_WARPS * 2 * 512 * p.cs + sizeof(GemmSmemCtl) +
+                        (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
     const int grid = (int)(g.num_super < num_sms ? g.num_super : num_sms);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to, tt;
     memcpy(&ta, p.tmap_a, sizeof ta);
     memcpy(&tb, p.tmap_b, sizeof tb);
-    if (p.u8) gemm_i8_tcgen05_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, (uint8_t*)out, g, e);
-    else gemm_i8_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, (uint8_t*)out, g, e);
-    return cudaGetLastError();
+    memcpy(&to, p.tmap_out, sizeof to);
+    memcpy(&tt, p.tmap_out_tail, sizeof tt);
+    const int mode = !e.fast_ok ? 2 : ((!p.u8 && e.fuse_bias) ? 1 : 0);
+    cudaError_t err = cudaErrorInvalidValue;
+#define TB200_GEMM_CASE(U, MD, C)                                                                                              \
+    if ((p.u8 != 0) == U && mode == MD && p.cs == C)                                                                           \
+    {                                                                                                                          \
+        static bool attr = false;                                                                                              \
+        if (!attr)                                                                                                             \
+        {                                                                                                                      \
+            err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            if (err != cudaSuccess) return err;                                                                                \
+            attr = true;                                                                                                       \
+        }                                                                                                                      \
+        gemm_i8_tcgen05_kernel<U, MD, C><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, to, tt, g, e);                              \
+        return cudaGetLastError();                                                                                             \
+    }
+#define TB200_GEMM_CS(U, MD) TB200_GEMM_CASE(U, MD, 1) TB200_GEMM_CASE(U, MD, 2) TB200_GEMM_CASE(U, MD, 4)
+    TB200_GEMM_CS(false, 0)
+    TB200_GEMM_CS(false, 1)
+    TB200_GEMM_CS(false, 2)
+    TB200_GEMM_CS(true, 0)
+    TB200_GEMM_CS(true, 2)
+#undef TB200_GEMM_CS
+#undef TB200_GEMM_CASE
+    return err;
 }
 
 } // namespace tb200

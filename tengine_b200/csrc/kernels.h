@@ -60,6 +60,8 @@ struct GemmPlan
 {
     alignas(64) unsigned char tmap_a[128]; // CUtensorMap
     alignas(64) unsigned char tmap_b[128];
+    alignas(64) unsigned char tmap_out[128];      // (C, rows, outer) over the output, box = 16*cs x 32 rows
+    alignas(64) unsigned char tmap_out_tail[128]; // same with rows_valid % 32 rows (last quarter of a short conv patch)
     long long m;
     int k;       // padded K (multiple of 16)
     int oc, ocp; // logical / padded output channels
@@ -72,13 +74,14 @@ struct GemmPlan
     int u8, bnx, taps, in_h, in_w; // uint8: B tiles carry 16 extra rows (ones-row -> per-pixel sum of x)
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
+    int cs, ngroups, rows_valid, out_mode; // epilogue store groups, see gemm_tcgen05.cu plan_epilogue
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
 int gemm_block_n(int ocp, int u8);
-int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, long long m, int k, int oc, int ocp, int ldo,
+int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, void* out, long long m, int k, int oc, int ocp, int ldo,
                      int variant, int u8);
-int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, const ConvShape& s, int u8);
-cudaError_t launch_gemm_i8(const GemmPlan& plan, void* out, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
+int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, void* out, const ConvShape& s, int u8);
+cudaError_t launch_gemm_i8(const GemmPlan& plan, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
 
 } // namespace tb200

@@ -202,48 +202,9 @@ __global__ void __launch_bounds__(128) conv_dw3x3_i8_kernel(const uint8_t* __res
     }
 
     uint8_t* orow = out + (((size_t)n * s.oh + oh) * s.ow + ow0) * s.ocp;
-    if (!e.fast_ok)
-    {
-#pragma unroll
-        for (int t = 0; t < TW; t++)
-            if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
-        return;
-    }
-    float m[4];
-    int32_t b[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-    {
-        const float2 p = __ldg(e.fast_par + c4 * 4 + j); // pad channels: (0, 0) -> output byte 0
-        m[j] = p.x, b[j] = __float_as_int(p.y);
-    }
-    uint32_t bad = 0;
-    uint32_t w[TW];
-#pragma unroll
-    for (int t = 0; t < TW; t++) w[t] = e.fuse_bias ? requant_fast4<false, true>(acc[t], e, m, b, bad, 1u << (4 * t)) : requant_fast4<false, false>(acc[t], e, m, b, bad, 1u << (4 * t));
-    if (bad)
-    {
-#pragma unroll 1
-        for (int i = 0; i < 4 * TW; i++)
-            if ((bad >> i) & 1u)
-            {
-                // dynamic register-array indexing would spill: select with a small unrolled switch
-                int32_t a = 0;
-                uint32_t word = 0;
-#pragma unroll
-                for (int t = 0; t < TW; t++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (i == t * 4 + j) a = acc[t][j], word = w[t];
-                word = requant_fix_byte(word, i & 3, a, c4 * 4 + (i & 3), e);
-#pragma unroll
-                for (int t = 0; t < TW; t++)
-                    if ((i >> 2) == t) w[t] = word;
-            }
-    }
 #pragma unroll
     for (int t = 0; t < TW; t++)
-        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = w[t];
+        if (ow0 + t < s.ow) reinterpret_cast<unsigned*>(orow + (size_t)t * s.ocp)[c4] = requant_word<false>(acc[t], c4 * 4, s.oc, e);
 }
 
 // ------------------------------------------------------------------------------------------------------

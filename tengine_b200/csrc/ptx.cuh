@@ -115,6 +115,28 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
         : "memory");
 }
 
+// ---- TMA stores (shared -> global through a tensor map; rows outside the tensor are clipped by the TMA unit) ----
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_addr, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 int tmap_encode(void* tmap, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                 const uint32_t* elem_strides, int swizzle_bytes);
