@@ -34,7 +34,8 @@ static constexpr int EPI_WARPS = 16; // four per TMEM lane quarter
 static constexpr int EPI_THREADS = EPI_WARPS * 32;
 static constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 static constexpr int PAR_MAX = 2048; // channels whose epilogue constants stay resident in smem for the whole kernel
-static constexpr int MAX_STAGES = 8;
+static constexpr int MAX_STAGES = 24;
+static constexpr int B_RESIDENT_MAX = 96 * 1024; // weights of the CTA's N tile stay in smem when they fit in this many bytes
 
 // K-major operand tile in shared memory, rows of `swizzle` bytes, 8-row groups `8*swizzle` bytes apart
 // (cute/atom/mma_traits_sm100.hpp: canonical layout ((8,n),2):((swizzle/16,SBO),1), LBO = 1, version 1).
@@ -83,6 +84,7 @@ struct GemmArgs
     int rows_valid;  // rows of an m-tile that are output pixels (128, or bw*bh*bn of a smaller conv patch)
     int out_mode;    // coordinates of the output map: 0 (c, row, 0)  1 (c, pixel in image, image)  2 (c, x, image row)
     int par_all;     // the constants of every channel are resident (loaded once); else reloaded per N tile
+    int b_res;       // the N tile's weights (all k-blocks) are loaded once and stay in smem; the ring carries A only
     const int32_t* btab; // [taps][OCp]: zx * (sum_c w[oc][tap][c] - Cin*zw), the correction a padding tap needs
 };
 
@@ -99,6 +101,7 @@ __device__ __forceinline__ void tile_origin(const GemmArgs& g, int mt, int& n0, 
 struct __align__(16) GemmSmemCtl
 {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    uint64_t b_full; // resident-B mode: all k-blocks of the N tile's weights have landed
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -249,9 +252,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // aligned: their TMA swizzle pattern is a function of the address), the control block and the epilogue constants
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.bnx * g.block_k;
-    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+    const uint32_t b_al = (b_bytes + 1023) & ~1023u;
+    const uint32_t stage_bytes = a_bytes + (g.b_res ? 0u : b_al);
+    uint8_t* b_region = smem + (size_t)g.stages * stage_bytes; // resident-B mode: [k_blocks][b_al]
     constexpr uint32_t buf_bytes = 512u * CS; // 32 rows x 16*CS bytes
-    uint8_t* stg = smem + (size_t)g.stages * stage_bytes;
+    uint8_t* stg = b_region + (g.b_res ? (size_t)g.k_blocks * b_al : 0);
     const uint32_t stg_base = smem_u32(stg);
     GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(stg + (size_t)EPI_WARPS * 2 * buf_bytes);
     const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl); // [par channels] x 8 bytes (see FastPar4)
@@ -263,6 +268,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     {
         for (int s = 0; s < g.stages; s++) mbar_init(&ctl->full[s], 1), mbar_init(&ctl->empty[s], 1);
         for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], EPI_WARPS);
+        mbar_init(&ctl->b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2)
@@ -287,6 +293,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
             int stage = 0;
             uint32_t phase = 0;
+            if (g.b_res)
+            {
+                // the grid is a multiple of n_tiles, so this CTA only ever sees N tile blockIdx.x % n_tiles: load its
+                // weights (every k-block) once
+                const int nb = (blockIdx.x % g.n_tiles) * g.bnx;
+                mbar_expect_tx(&ctl->b_full, (uint32_t)g.k_blocks * b_bytes);
+                for (int kb = 0; kb < g.k_blocks; kb++)
+                {
+                    const int kc = g.conv ? (kb / g.cblocks) * g.cp + (kb % g.cblocks) * g.block_k : kb * g.block_k;
+                    tma_load_2d(&tmap_b, &ctl->b_full, b_region + (size_t)kb * b_al, kc, nb);
+                }
+            }
             for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
                 const int msup = st / g.n_tiles;
@@ -304,9 +322,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         if (!g.conv)
                         {
-                            mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+                            mbar_expect_tx(&ctl->full[stage], a_bytes + (g.b_res ? 0u : b_bytes));
                             tma_load_2d(&tmap_a, &ctl->full[stage], sa, kb * g.block_k, m0);
-                            tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
+                            if (!g.b_res) tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, kb * g.block_k, n0);
                         }
                         else
                         {
@@ -314,10 +332,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             // coordinates outside the image are zero-filled by the TMA unit = the convolution's padding
                             const int tap = kb / g.cblocks, cb = kb - tap * g.cblocks;
                             const int kh = tap / g.kw_n, kw = tap - kh * g.kw_n;
-                            mbar_expect_tx(&ctl->full[stage], g.a_tx_bytes + b_bytes);
+                            mbar_expect_tx(&ctl->full[stage], g.a_tx_bytes + (g.b_res ? 0u : b_bytes));
                             tma_load_4d(&tmap_a, &ctl->full[stage], sa, cb * g.block_k, cow0 * g.cstride - g.pad_w + kw,
                                         coh0 * g.cstride - g.pad_h + kh, cn0);
-                            tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, tap * g.cp + cb * g.block_k, n0);
+                            if (!g.b_res) tma_load_2d(&tmap_b, &ctl->full[stage], sa + a_bytes, tap * g.cp + cb * g.block_k, n0);
                         }
                         if (++stage == g.stages) stage = 0, phase ^= 1;
                     }
@@ -334,6 +352,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+            if (g.b_res) mbar_wait(&ctl->b_full, 0);
             for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
             {
                 const int mt0 = (st / g.n_tiles) * g.mt;
@@ -347,7 +366,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         mbar_wait(&ctl->full[stage], phase); // TMA bytes have landed
                         tcgen05_fence_after();
                         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                        const uint64_t da = make_smem_desc(sa, g.swizzle), db = make_smem_desc(sa + a_bytes, g.swizzle);
+                        const uint32_t sb = g.b_res ? smem_u32(b_region) + (uint32_t)kb * b_al : sa + a_bytes;
+                        const uint64_t da = make_smem_desc(sa, g.swizzle), db = make_smem_desc(sb, g.swizzle);
                         for (int k = 0; k < g.block_k / 32; k++)
                         {
                             // advance 32 bytes (one UMMA_K of int8) inside the swizzled row: +2 in 16-byte units
@@ -588,6 +608,22 @@ static int epilogue_smem_bytes(const GemmPlan* p)
     return EPI_WARPS * 2 * 512 * 4 /* staging at the widest cs */ + (par_ch <= PAR_MAX ? par_ch : p->block_n) * 8 + (int)sizeof(GemmSmemCtl) + 2048;
 }
 
+// Operand ring depth and the resident-B decision.  With the N tile's weights resident the ring carries A tiles only,
+// which for the small-K layers (K = 32..128, one 4-16 KB A tile per m-tile) is the difference between 8 and 24 m-tiles
+// of prefetch distance.
+static int plan_ring(GemmPlan* p)
+{
+    const int a_bytes = BLOCK_M * p->block_k, b_al = (p->bnx * p->block_k + 1023) & ~1023;
+    const int budget = 224 * 1024 - epilogue_smem_bytes(p);
+    p->b_res = ((long long)p->k_blocks * b_al <= B_RESIDENT_MAX && !getenv("TB200_GEMM_NO_BRES")) ? 1 : 0;
+    int stages = p->b_res ? (budget - p->k_blocks * b_al) / a_bytes : budget / (a_bytes + b_al);
+    if (p->b_res && stages < 3) p->b_res = 0, stages = budget / (a_bytes + b_al);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return TB200_ERR_INVALID;
+    p->stages = stages;
+    return 0;
+}
+
 int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, void* out, long long m, int k, int oc, int ocp, int ldo,
                      int variant, int u8)
 {
@@ -603,16 +639,13 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
     p->taps = 1;
     p->n_tiles = (ocp + p->block_n - 1) / p->block_n;
     p->m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
-    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->bnx * p->block_k + 1023) & ~1023;
     // m-tiles per accumulator stage: amortise the per-stage synchronisation over ~256 TMEM columns of work
     p->mt = 1;
     if (p->n_tiles == 1)
         while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
-    int stages = (224 * 1024 - epilogue_smem_bytes(p)) / (a_bytes + b_bytes);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return TB200_ERR_INVALID;
-    p->stages = stages;
-    int rc = encode_2d(p->tmap_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, p->block_k, BLOCK_M, p->swizzle);
+    int rc = plan_ring(p);
+    if (rc) return rc;
+    rc = encode_2d(p->tmap_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, p->block_k, BLOCK_M, p->swizzle);
     if (rc) return rc;
     rc = encode_2d(p->tmap_b, b, (uint64_t)k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)k, p->block_k, p->bnx, p->swizzle);
     if (rc) return rc;
@@ -659,20 +692,17 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out,
     p->m_tiles = (long long)p->tiles_w * p->tiles_h * tiles_n;
     p->kw_n = s.kw, p->pad_h = s.ph0, p->pad_w = s.pw0, p->cstride = s.sh, p->cp = s.cp, p->oh = s.oh, p->ow = s.ow, p->nimg = s.n;
     p->a_tx_bytes = (uint32_t)(p->block_k * p->bw * p->bh * p->bn);
-    const int a_bytes = BLOCK_M * p->block_k, b_bytes = (p->bnx * p->block_k + 1023) & ~1023;
     p->mt = 1;
     if (p->n_tiles == 1)
         while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
-    int stages = (224 * 1024 - epilogue_smem_bytes(p)) / (a_bytes + b_bytes);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return TB200_ERR_INVALID;
-    p->stages = stages;
+    int rc = plan_ring(p);
+    if (rc) return rc;
     const uint64_t dims[4] = {(uint64_t)s.cp, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
     const uint64_t strides[3] = {(uint64_t)s.cp, (uint64_t)s.w * s.cp, (uint64_t)s.h * s.w * s.cp};
     const uint32_t box[4] = {(uint32_t)p->block_k, (uint32_t)((p->bw - 1) * s.sw + 1), (uint32_t)((p->bh - 1) * s.sh + 1), (uint32_t)p->bn};
     const uint32_t estr[4] = {1u, (uint32_t)s.sw, (uint32_t)s.sh, 1u};
     if (box[1] > 256 || box[2] > 256 || box[3] > 256) return TB200_ERR_UNSUPPORTED;
-    int rc = tmap_encode(p->tmap_a, in, 4, dims, strides, box, estr, p->swizzle);
+    rc = tmap_encode(p->tmap_a, in, 4, dims, strides, box, estr, p->swizzle);
     if (rc) return rc;
     rc = encode_2d(p->tmap_b, w, (uint64_t)p->k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)p->k, p->block_k, p->bnx, p->swizzle);
     if (rc) return rc;
@@ -717,9 +747,12 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     const int par_ch = p.n_tiles * p.block_n;
     g.par_all = par_ch <= PAR_MAX ? 1 : 0;
     const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.bnx * p.block_k + 1023) & ~1023;
-    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + (size_t)EPI_WARPS * 2 * 512 * p.cs + sizeof(GemmSmemCtl) +
+    g.b_res = p.b_res;
+    const size_t smem = (size_t)p.stages * (a_bytes + (p.b_res ? 0 : b_bytes)) + (p.b_res ? (size_t)p.k_blocks * b_bytes : 0) +
+                        (size_t)EPI_WARPS * 2 * 512 * p.cs + sizeof(GemmSmemCtl) +
                         (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
-    const int grid = (int)(g.num_super < num_sms ? g.num_super : num_sms);
+    int grid = (int)(g.num_super < num_sms ? g.num_super : num_sms);
+    if (p.b_res) grid -= grid % p.n_tiles; // a CTA must see one N tile only (num_super is a multiple of n_tiles, so grid >= n_tiles)
     CUtensorMap ta, tb, to, tt;
     memcpy(&ta, p.tmap_a, sizeof ta);
     memcpy(&tb, p.tmap_b, sizeof tb);

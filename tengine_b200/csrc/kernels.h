@@ -75,6 +75,7 @@ struct GemmPlan
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
     int cs, ngroups, rows_valid, out_mode; // epilogue store groups, see gemm_tcgen05.cu plan_epilogue
+    int b_res;                             // weights of the N tile resident in smem (ring carries A only)
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
