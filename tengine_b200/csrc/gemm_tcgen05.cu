@@ -246,7 +246,9 @@ __device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int 
 }
 
 // MODE: 0 fast epilogue, 1 fast epilogue with the bias folded into the FMA (int8 only), 2 exact epilogue.
-// CS: 16-column chunks per store group (1, 2 or 4).  Compile-time so that each kernel carries exactly one epilogue body.
+// CS: 16-column chunks per store group (1, 2, 4 or 8).  Compile-time so that each kernel carries exactly one epilogue body.
+// CS == 8: a group is 32 rows x 128 bytes filled by a PAIR of warps (64 bytes each) and stored by one of them: the TMA
+// unit's cost is per row (~4 cycles for anything up to 128 bytes), so 128-byte rows halve the store side's share of it.
 template <bool U8, int MODE, int CS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -262,9 +264,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const uint32_t stage_bytes = a_bytes + (g.b_res ? 0u : b_al);
     uint8_t* b_region = smem + (size_t)g.stages * stage_bytes; // resident-B mode: [k_blocks][b_al]
     constexpr uint32_t buf_bytes = 512u * CS; // 32 rows x 16*CS bytes
+    constexpr int WCH = CS == 8 ? 4 : CS;     // chunks one warp requantises per group
     uint8_t* stg = b_region + (g.b_res ? (size_t)g.k_blocks * b_al : 0);
     const uint32_t stg_base = smem_u32(stg);
-    GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(stg + (size_t)EPI_WARPS * 2 * buf_bytes);
+    GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(stg + (size_t)(CS == 8 ? EPI_WARPS / 2 : EPI_WARPS) * 2 * buf_bytes);
     const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl); // [par channels] x 8 bytes (see FastPar4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -412,10 +415,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         int qrows = g.rows_valid - q * 32; // rows of this quarter that are output pixels
         qrows = qrows < 0 ? 0 : (qrows > 32 ? 32 : qrows);
         const CUtensorMap* tm_out = (qrows == 32) ? &tmap_out : &tmap_out_tail;
-        const uint32_t buf0 = stg_base + (uint32_t)warp * 2u * buf_bytes;
-        // swizzle of the staging buffer = the output map's swizzle: 16-byte chunk index ^= row bits (Swizzle<1|2,4,3>)
-        const uint32_t xl = CS == 4 ? (uint32_t)((lane >> 1) & 3) << 4 : (CS == 2 ? (uint32_t)((lane >> 2) & 1) << 4 : 0u);
+        const int half = CS == 8 ? (sub & 1) : 0;        // which 64-byte half of the pair's 128-byte rows this warp fills
+        const int pair = q * 2 + (sub >> 1);             // CS == 8: staging buffers and the named barrier are per pair
+        const uint32_t buf0 = stg_base + (uint32_t)(CS == 8 ? pair : warp) * 2u * buf_bytes;
+        // swizzle of the staging buffer = the output map's swizzle: 16-byte chunk index ^= row bits (Swizzle<1|2|3,4,3>)
+        const uint32_t xl = CS == 8   ? (uint32_t)(lane & 7) << 4
+                            : CS == 4 ? (uint32_t)((lane >> 1) & 3) << 4
+                                      : (CS == 2 ? (uint32_t)((lane >> 2) & 1) << 4 : 0u);
         const uint32_t row_off = (uint32_t)lane * 16u * CS;
+        const int gfirst = CS == 8 ? (sub >> 1) : sub, gstep = CS == 8 ? 2 : 4; // groups are dealt to pairs / warps
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); };
         uint32_t ucount = 0; // groups this warp has stored (buffer parity)
         const int par_ch = g.n_tiles * g.block_n;
         const bool fast = MODE != 2;
@@ -453,16 +462,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             {
                 // groups of this warp: flattened index u = i * ngroups + grp, u = sub, sub + 4, ...
                 uint32_t v0[16], v1[16];
-                int i = 0, grp = sub;
+                int i = 0, grp = gfirst;
                 while (grp >= ngroups) grp -= ngroups, i++;
-                if (CS > 1 && i < mtc) tmem_ld16(tbase + i * g.bnx + grp * (CS * 16), v0);
+                if (CS > 1 && i < mtc) tmem_ld16(tbase + i * g.bnx + grp * (CS * 16) + half * 64, v0);
                 while (i < mtc)
                 {
-                    int i2 = i, g2 = grp + 4; // the group after this one
+                    int i2 = i, g2 = grp + gstep; // the group after this one
                     while (g2 >= ngroups) g2 -= ngroups, i2++;
                     const uint32_t buf = buf0 + (ucount & 1u) * buf_bytes;
-                    if (lane == 0) bulk_wait_read<1>(); // the store issued two groups ago has finished reading this buffer
-                    __syncwarp();
+                    // the store issued two groups ago has finished reading this buffer
+                    if (lane == 0 && half == 0) bulk_wait_read<1>();
+                    if (CS == 8) pair_sync();
+                    else __syncwarp();
                     int32_t sx = 0;
                     uint64_t pad = 0;
                     if (U8)
@@ -471,13 +482,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
                         pad = padding_taps(g, mt0 + i, q * 32 + lane);
                     }
-                    const uint32_t tg = tbase + i * g.bnx + grp * (CS * 16);
+                    const uint32_t tg = tbase + i * g.bnx + grp * (CS * 16) + half * 64;
                     const int cg0 = grp * (CS * 16); // first column of the group inside the N tile
                     const uint32_t sdst = buf + row_off;
                     auto unit = [&](const uint32_t (&v)[16], int k)
                     {
-                        const int c = cg0 + k * 16;
-                        const uint32_t dst = sdst + (((uint32_t)k << 4) ^ xl);
+                        const int c = cg0 + half * 64 + k * 16;
+                        const uint32_t dst = sdst + (((uint32_t)(half * 4 + k) << 4) ^ xl);
                         if (U8) epilogue_unit_u8<MODE == 2>(v, sx, pad, g, par_s + c * 8, dst, n0 + c, e);
                         else if (MODE == 2) epilogue_unit_exact(v, dst, n0 + c, g.oc, e);
                         else epilogue_unit_fast<MODE == 1>(v, par_s + c * 8, dst, n0 + c, e);
@@ -491,20 +502,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     else
                     {
 #pragma unroll
-                        for (int k = 0; k < CS; k++)
+                        for (int k = 0; k < WCH; k++)
                         {
                             tmem_ld_wait();
                             if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 3);
                             // the next chunk's accumulators are in flight while this one is requantised
-                            if (k + 1 < CS) tmem_ld16(tg + (k + 1) * 16, (k & 1) ? v0 : v1);
-                            else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16), v0);
+                            if (k + 1 < WCH) tmem_ld16(tg + (k + 1) * 16, (k & 1) ? v0 : v1);
+                            else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16) + half * 64, v0);
                             unit((k & 1) ? v1 : v0, k);
                             if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 4);
                         }
                     }
                     fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA unit
-                    __syncwarp();
-                    if (lane == 0)
+                    if (CS == 8) pair_sync();
+                    else __syncwarp();
+                    if (lane == 0 && half == 0)
                     {
                         int x1, x2 = 0;
                         if (!g.conv)
@@ -605,6 +617,10 @@ static void plan_store_groups(GemmPlan* p)
             cs = c;
             break;
         }
+    // 128-byte rows filled by warp pairs when the stage deals an even number of 128-column groups to each quarter
+    // (measured on MobileNet-v1, batch 256: the pair hand-over costs more than the halved row count saves -- 0.75 ms vs
+    //  0.68 ms for all GEMMs -- so this mode is opt-in)
+    if (nch % 8 == 0 && (p->mt * (nch / 8)) % 2 == 0 && getenv("TB200_GEMM_PAIR")) cs = 8;
     if (const char* ev = getenv("TB200_GEMM_STORE_CS"))
     {
         const int f = atoi(ev);
@@ -618,7 +634,7 @@ static int plan_epilogue(GemmPlan* p, const void* out, uint64_t d1, uint64_t d2)
     const int cs = p->cs;
     const uint64_t dims[3] = {(uint64_t)p->ocp, d1, d2};
     const uint64_t strides[2] = {(uint64_t)p->ldo, (uint64_t)p->ldo * d1};
-    const int swz = cs == 4 ? 64 : (cs == 2 ? 32 : 0);
+    const int swz = cs == 8 ? 128 : (cs == 4 ? 64 : (cs == 2 ? 32 : 0));
     const uint32_t box[3] = {(uint32_t)(16 * cs), 32u, 1u};
     int rc = tmap_encode(p->tmap_out, out, 3, dims, strides, box, nullptr, swz);
     if (rc) return rc;
@@ -631,7 +647,7 @@ static int plan_epilogue(GemmPlan* p, const void* out, uint64_t d1, uint64_t d2)
 static int epilogue_smem_bytes(const GemmPlan* p)
 {
     const int par_ch = p->n_tiles * p->block_n;
-    return EPI_WARPS * 2 * 512 * p->cs + (par_ch <= PAR_MAX ? par_ch : p->block_n) * 8 + (int)sizeof(GemmSmemCtl) + 2048;
+    return EPI_WARPS * 2 * 512 * (p->cs == 8 ? 4 : p->cs) + (par_ch <= PAR_MAX ? par_ch : p->block_n) * 8 + (int)sizeof(GemmSmemCtl) + 2048;
 }
 
 // Operand ring depth and the resident-B decision.  With the N tile's weights resident the ring carries A tiles only,
@@ -667,8 +683,12 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
     p->m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
     // m-tiles per accumulator stage: amortise the per-stage synchronisation over ~256 TMEM columns of work
     p->mt = 1;
-    if (p->n_tiles == 1)
-        while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+    {
+        // several m-tiles per stage when the CTA stays on one N tile anyway (single tile, or resident weights)
+        const bool resident = (long long)p->k_blocks * ((p->bnx * p->block_k + 1023) & ~1023) <= B_RESIDENT_MAX;
+        if (p->n_tiles == 1 || (resident && getenv("TB200_GEMM_PAIR")))
+            while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) * 148 <= p->m_tiles * (p->n_tiles == 1 ? 148 : 1)) p->mt *= 2;
+    }
     plan_store_groups(p);
     int rc = plan_ring(p);
     if (rc) return rc;
@@ -720,8 +740,12 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out,
     p->kw_n = s.kw, p->pad_h = s.ph0, p->pad_w = s.pw0, p->cstride = s.sh, p->cp = s.cp, p->oh = s.oh, p->ow = s.ow, p->nimg = s.n;
     p->a_tx_bytes = (uint32_t)(p->block_k * p->bw * p->bh * p->bn);
     p->mt = 1;
-    if (p->n_tiles == 1)
-        while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) <= p->m_tiles) p->mt *= 2;
+    {
+        // several m-tiles per stage when the CTA stays on one N tile anyway (single tile, or resident weights)
+        const bool resident = (long long)p->k_blocks * ((p->bnx * p->block_k + 1023) & ~1023) <= B_RESIDENT_MAX;
+        if (p->n_tiles == 1 || (resident && getenv("TB200_GEMM_PAIR")))
+            while (p->mt < 4 && 2 * (p->mt * 2) * p->bnx <= 512 && (long long)(p->mt * 2) * 148 <= p->m_tiles * (p->n_tiles == 1 ? 148 : 1)) p->mt *= 2;
+    }
     plan_store_groups(p);
     int rc = plan_ring(p);
     if (rc) return rc;
@@ -802,7 +826,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.bnx * p.block_k + 1023) & ~1023;
     g.b_res = p.b_res;
     const size_t smem = (size_t)p.stages * (a_bytes + (p.b_res ? 0 : b_bytes)) + (p.b_res ? (size_t)p.k_blocks * b_bytes : 0) +
-                        (size_t)EPI_WARPS * 2 * 512 * p.cs + sizeof(GemmSmemCtl) +
+                        (size_t)EPI_WARPS * 2 * 512 * (p.cs == 8 ? 4 : p.cs) + sizeof(GemmSmemCtl) +
                         (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
     static const bool trace_on = getenv("TB200_GEMM_TRACE") != nullptr;
     static unsigned long long* trace_buf = nullptr;
@@ -836,7 +860,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
         if (trace_on) gemm_trace_report(p, g, grid, st);                                                                       \
         return cudaGetLastError();                                                                                             \
     }
-#define TB200_GEMM_CS(U, MD) TB200_GEMM_CASE(U, MD, 1) TB200_GEMM_CASE(U, MD, 2) TB200_GEMM_CASE(U, MD, 4)
+#define TB200_GEMM_CS(U, MD) TB200_GEMM_CASE(U, MD, 1) TB200_GEMM_CASE(U, MD, 2) TB200_GEMM_CASE(U, MD, 4) TB200_GEMM_CASE(U, MD, 8)
     TB200_GEMM_CS(false, 0)
     TB200_GEMM_CS(false, 1)
     TB200_GEMM_CS(false, 2)
