@@ -17,6 +17,10 @@ namespace tb200 {
 
 static constexpr int DW_THREADS = 128;
 static constexpr int DW_CH = 32; // channels per CTA (8 words)
+#ifndef TB200_DW_MIN_CTAS
+#define TB200_DW_MIN_CTAS 6
+#endif
+static constexpr int DW_MIN_CTAS = TB200_DW_MIN_CTAS; // 6 caps the kernels at 80 registers and spills (ptxas: 32-byte stack)
 
 // Fused epilogue of both kernels: TW pixels x 4 channels per thread.  The accumulators were initialised with
 // TB200_MAGIC_BITS (|sum of 9 products| < 2^22), so the int->float conversion is a packed FADD on the FMA pipe
@@ -66,7 +70,7 @@ __device__ __forceinline__ void dw_epilogue(int (&acc)[TW][4], const FastPar4& f
 }
 
 template <int TW, int S>
-__global__ void __launch_bounds__(DW_THREADS, 6)
+__global__ void __launch_bounds__(DW_THREADS, DW_MIN_CTAS)
     conv_dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out,
                           const ConvShape s, const __grid_constant__ EpiParams e, const int rows_per_cta, const int gpr, const int tile_cols,
                           const int tile_rows)
@@ -150,7 +154,7 @@ __device__ __forceinline__ void transpose4x4(unsigned x0, unsigned x1, unsigned 
     ch[2] = __byte_perm(t2, t3, 0x5410), ch[3] = __byte_perm(t2, t3, 0x7632);
 }
 
-__global__ void __launch_bounds__(DW_THREADS, 6)
+__global__ void __launch_bounds__(DW_THREADS, DW_MIN_CTAS)
     conv_dw3x3_tma_pack3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ out,
                                 const ConvShape s, const __grid_constant__ EpiParams e, const int rows_per_cta, const int gpr,
                                 const int tile_cols, const int tile_rows)

@@ -49,6 +49,7 @@ enum StepKind
     K_NCHW2NHWC,
     K_NHWC2NCHW,
     K_CONV_STEM,
+    K_STEM_TC,
     K_CONV_DW,
     K_CONV_DIRECT,
     K_GEMM,
@@ -59,7 +60,7 @@ enum StepKind
     K_UPSAMPLE,
     K_COPY
 };
-static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_dw_direct", "conv_direct_dp4a",
+static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_stem_nchw_tcgen05", "conv_dw_direct", "conv_direct_dp4a",
                                   "gemm_i8_tcgen05", "conv_igemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy"};
 
 struct Step
@@ -271,6 +272,7 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_NCHW2NHWC: err = launch_nchw_to_nhwc(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_NHWC2NCHW: err = launch_nhwc_to_nchw(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_CONV_STEM: err = launch_conv_stem(s.in, s.w, s.out, s.cs, s.epi, st); break;
+    case K_STEM_TC: err = launch_stem_tc(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_CONV_DW:
         err = s.dwp.valid ? launch_conv_dw_tma(s.dwp, s.w, s.out, s.cs, s.epi, st) : launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st);
         break;
@@ -378,7 +380,10 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 return bail(fail(TB200_ERR_INVALID, "layer %d: conv output shape %dx%d does not match descriptor %dx%d", li, oh, ow, tout.d.dims[2], tout.d.dims[3]));
             const int cg = C / L.group;
             size_t wsize;
-            if (tin.input_index >= 0 && C <= 4 && L.group == 1)
+            if (tin.input_index >= 0 && C <= 3 && L.group == 1 && !u8 && !no_tc && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
+                L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_STEM_TC"))
+                kind[li] = K_STEM_TC, wsize = (size_t)tout.cp * 32; // one 32-byte UMMA k-step per output channel
+            else if (tin.input_index >= 0 && C <= 4 && L.group == 1)
                 kind[li] = K_CONV_STEM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * 4;
             else if (L.group == C && OC == C && C > 1)
                 kind[li] = K_CONV_DW, wsize = (size_t)L.kernel_h * L.kernel_w * tin.cp;
@@ -444,7 +449,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
-            if (g->tensors[L.inputs[k]].input_index >= 0 && kind[li] != K_CONV_STEM) g->tensors[L.inputs[k]].nhwc_needed = true;
+            if (g->tensors[L.inputs[k]].input_index >= 0 && kind[li] != K_CONV_STEM && kind[li] != K_STEM_TC) g->tensors[L.inputs[k]].nhwc_needed = true;
     }
     for (int id : g->output_ids)
         if (g->tensors[id].input_index >= 0) g->tensors[id].nhwc_needed = true;
@@ -544,6 +549,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 {
                     for (int c = 0; c < C; c++)
                         for (int t = 0; t < KH * KW; t++) dst[(size_t)t * tin.cp + c] = src[(size_t)c * KH * KW + t];
+                }
+                else if (kind[li] == K_STEM_TC)
+                {
+                    // [OC][C][3][3] is already k = (c*3 + kh)*3 + kw order: one zero-padded 32-byte row per channel
+                    for (int o = 0; o < OC; o++) memcpy(dst + (size_t)o * 32, src + (size_t)o * C * 9, (size_t)C * 9);
                 }
                 else
                 {
@@ -693,7 +703,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
                     }
                 }
-                if (s.kind == K_CONV_STEM) s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
+                if (s.kind == K_CONV_STEM || s.kind == K_STEM_TC) s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)
                 {

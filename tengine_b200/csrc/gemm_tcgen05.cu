@@ -30,6 +30,12 @@
 
 namespace tb200 {
 
+#ifdef TB200_GEMM_TIMELINE
+#define TLOG_E(tag) do { if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, tag); } while (0)
+#else
+#define TLOG_E(tag) do { } while (0)
+#endif
+
 static constexpr int BLOCK_M = 128;
 static constexpr int EPI_WARPS = 16; // four per TMEM lane quarter
 static constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -273,11 +279,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int acc_cols = g.mt * g.bnx; // TMEM columns of one accumulator stage
     // debug timeline: CTA 0 only, 4 logs x 1024 events of (clock << 8 | tag); plain global stores, no atomics
+#ifdef TB200_GEMM_TIMELINE
     int tl_n = 0;
     auto tlog = [&](int role, int tag)
     {
         if (g.trace && blockIdx.x == 0 && tl_n < 1024) g.trace[role * 1024 + tl_n++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
     };
+#else
+    auto tlog = [](int, int) {}; // the timeline costs instructions in the epilogue's inner loop: debug builds only
+#endif
 
     if (threadIdx.x == 0)
     {
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 par_s = par_base;
             }
             mbar_wait(&ctl->tmem_full[as], aphase);
-            if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 0);
+            TLOG_E(0);
             tcgen05_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
             if (qrows > 0)
@@ -505,12 +515,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         for (int k = 0; k < WCH; k++)
                         {
                             tmem_ld_wait();
-                            if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 3);
+                            TLOG_E(3);
                             // the next chunk's accumulators are in flight while this one is requantised
                             if (k + 1 < WCH) tmem_ld16(tg + (k + 1) * 16, (k & 1) ? v0 : v1);
                             else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16) + half * 64, v0);
                             unit((k & 1) ? v1 : v0, k);
-                            if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 4);
+                            TLOG_E(4);
                         }
                     }
                     fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA unit
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         tma_store_3d(tm_out, buf, n0 + cg0, x1 + q * 32, x2);
                         bulk_commit();
                     }
-                    if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 1);
+                    TLOG_E(1);
                     ucount++;
                     i = i2, grp = g2;
                 }
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]); // accumulator drained: the MMA warp may overwrite it
-            if (lane == 0 && (warp == 0 || warp == 15)) tlog(warp == 0 ? 2 : 3, 2);
+            TLOG_E(2);
             if (++as == 2) as = 0, aphase ^= 1;
         }
         if (lane == 0) bulk_wait<0>(); // all of this warp's stores have completed
@@ -552,6 +562,208 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
     }
+}
+
+// ---- stem on the tensor cores ------------------------------------------------------------------------------
+// First convolution of a network: NCHW int8 input with C <= 3 channels (as the application hands it over), 3x3 filter,
+// any stride / padding -> NHWC output.  K = C*9 <= 27 is padded to ONE 32-byte UMMA k-step: the 128 threads of a CTA
+// each gather the 27 input bytes of one output pixel, write them as one row of a SW32 K-major A tile, one thread issues
+// a single tcgen05.mma (128 x OCp x 32), and every thread requantises "its" TMEM lane and writes OCp contiguous bytes.
+// Replaces ~290 dp4a per pixel of the CUDA-core stem kernel (kernels_direct.cu) by one MMA; the work left is the gather
+// (~80 instructions) and the epilogue.  Several CTAs per SM (5 KB smem, OCp TMEM columns each) overlap each other.
+// Takes the role of the first im2col + sgemm of conv_hcl_run (conv_kernel_x86.c:187-242).
+struct StemArgs
+{
+    const uint8_t* in;  // NCHW
+    const uint8_t* w;   // [OCp][32]: k = (c*3 + kh)*3 + kw, zero padded
+    uint8_t* out;       // NHWC, OCp bytes per pixel
+    int n, c, h, w_in, oh, ow, ocp, oc, stride, ph, pw;
+    unsigned npix, ntiles;
+    uint32_t idesc, tmem_cols;
+};
+
+template <bool FUSE>
+__device__ __forceinline__ void stem_unit_fast(const uint32_t (&v)[16], uint32_t par_addr, int oc0, const EpiParams& e, uint32_t (&w)[4])
+{
+    float gw[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        float4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = lds_f4(par_addr + h * 64 + k * 16);
+        const int32_t a8[8] = {(int32_t)v[h * 8], (int32_t)v[h * 8 + 1], (int32_t)v[h * 8 + 2], (int32_t)v[h * 8 + 3],
+                               (int32_t)v[h * 8 + 4], (int32_t)v[h * 8 + 5], (int32_t)v[h * 8 + 6], (int32_t)v[h * 8 + 7]};
+        requant_fast8_i8<FUSE>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
+    }
+    if (e.q_byte_add)
+    {
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
+    }
+    if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
+    {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (gw[j] > 0.5f - TB200_TIE_EPS)
+                w[j] = requant_fix_word<FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, e);
+    }
+}
+
+// row r, 16-byte chunk c16 of a SW32 K-major tile (8-row groups of 256 bytes, chunk index ^= bit 2 of the row)
+__device__ __forceinline__ uint32_t sw32_offset(int r, int c16) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 32 + ((c16 ^ ((r >> 2) & 1)) << 4)); }
+
+template <int MODE> // 0 fast, 1 fast + fused bias, 2 exact
+__global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __grid_constant__ EpiParams e)
+{
+    extern __shared__ __align__(1024) uint8_t stem_smem[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stem_smem) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sA = smem_u32(sm), sB = sA + 4096, sPar = sB + (uint32_t)a.ocp * 32u;
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0)
+    {
+        mbar_init(&mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- B tile and the epilogue constants (identical for every CTA; L2 / L1 resident) ----
+    for (int i = tid; i < a.ocp * 2; i += 128)
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w) + i);
+        sts_u4(sB + sw32_offset(i >> 1, i & 1), v.x, v.y, v.z, v.w);
+    }
+    for (int c = tid; c < a.ocp; c += 128) sts_f2(sPar + c * 8, (MODE != 2) ? __ldg(e.fast_par + c) : make_float2(0.f, 0.f));
+
+    uint32_t phase = 0;
+    uint32_t tmem_base = 0;
+    for (unsigned tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    {
+        // ---- A row of this thread's pixel: gather the 3x3 x C window from the NCHW planes ----
+        const unsigned pix = tile * 128u + (unsigned)tid;
+        uint32_t row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (pix < a.npix)
+        {
+            const unsigned prow = pix / (unsigned)a.ow;
+            const int ow = (int)(pix - prow * a.ow);
+            const int n = (int)(prow / (unsigned)a.oh);
+            const int oh = (int)(prow - (unsigned)n * a.oh);
+            const int iy0 = oh * a.stride - a.ph, ix0 = ow * a.stride - a.pw;
+            const size_t plane = (size_t)a.h * a.w_in;
+            const uint8_t* img = a.in + (size_t)n * a.c * plane;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+            {
+                if (c < a.c)
+                {
+#pragma unroll
+                    for (int kh = 0; kh < 3; kh++)
+                    {
+                        const int iy = iy0 + kh;
+                        const bool rok = iy >= 0 && iy < a.h;
+                        const uint8_t* rp = img + (size_t)c * plane + (size_t)(rok ? iy : 0) * a.w_in;
+#pragma unroll
+                        for (int kw = 0; kw < 3; kw++)
+                        {
+                            const int ix = ix0 + kw;
+                            const uint32_t b = (rok && ix >= 0 && ix < a.w_in) ? (uint32_t)__ldg(rp + ix) : 0u;
+                            const int k = (c * 3 + kh) * 3 + kw; // compile-time after unrolling
+                            row[k >> 2] |= b << (8 * (k & 3));
+                        }
+                    }
+                }
+            }
+        }
+        sts_u4(sA + sw32_offset(tid, 0), row[0], row[1], row[2], row[3]);
+        sts_u4(sA + sw32_offset(tid, 1), row[4], row[5], row[6], row[7]);
+        fence_proxy_async_smem(); // the MMA reads these generic-proxy writes through the async proxy
+        tcgen05_fence_before();
+        __syncthreads(); // (first iteration: also publishes the TMEM address, the B tile and the constants)
+        tcgen05_fence_after();
+        tmem_base = tmem_slot;
+        if (tid == 0)
+        {
+            umma_i8(tmem_base, make_smem_desc(sA, 32), make_smem_desc(sB, 32), a.idesc, 0u);
+            tcgen05_commit(&mma_done);
+        }
+        mbar_wait(&mma_done, phase);
+        phase ^= 1;
+        tcgen05_fence_after();
+
+        // ---- epilogue: lane = pixel, 16 channels per TMEM load, OCp contiguous output bytes per pixel ----
+        uint8_t* op = a.out + (size_t)pix * a.ocp;
+        const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < a.ocp; c += 16)
+        {
+            uint32_t v[16];
+            tmem_ld16(tb + c, v);
+            tmem_ld_wait();
+            uint32_t w[4];
+            if (MODE == 2)
+            {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    if ((k & 3) == 0) w[k >> 2] = 0;
+                    if (c + k < a.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], c + k, e) & 0xffu) << (8 * (k & 3));
+                }
+            }
+            else
+                stem_unit_fast<MODE == 1>(v, sPar + c * 8, c, e, w);
+            if (pix < a.npix) *reinterpret_cast<uint4*>(op + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // the next tile's MMA overwrites the accumulator and its gather overwrites the A tile (the MMA has completed)
+        tcgen05_fence_before();
+        __syncthreads();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0)
+    {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+bool stem_tc_supported(const ConvShape& s, const EpiParams& e)
+{
+    return !e.is_uint8 && s.kh == 3 && s.kw == 3 && s.c <= 3 && s.group == 1 && s.dh == 1 && s.dw == 1 && s.sh == s.sw && s.ocp <= 256 &&
+           (long long)s.n * s.oh * s.ow < (1ll << 31);
+}
+
+cudaError_t launch_stem_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+{
+    StemArgs a;
+    a.in = (const uint8_t*)in, a.w = (const uint8_t*)w, a.out = (uint8_t*)out;
+    a.n = s.n, a.c = s.c, a.h = s.h, a.w_in = s.w, a.oh = s.oh, a.ow = s.ow, a.ocp = s.ocp, a.oc = s.oc, a.stride = s.sh, a.ph = s.ph0, a.pw = s.pw0;
+    a.npix = (unsigned)((long long)s.n * s.oh * s.ow);
+    a.idesc = make_idesc_i8(s.ocp, true, true);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)s.ocp) cols <<= 1;
+    a.tmem_cols = cols;
+    const size_t smem = 4096 + (size_t)s.ocp * 32 + (size_t)s.ocp * 8 + 1024;
+    a.ntiles = (a.npix + 127u) / 128u;
+    static int sms = 0;
+    if (!sms)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // several resident CTAs per SM overlap gather / MMA / epilogue of different tiles; each loops over its share
+    const unsigned cap = (unsigned)sms * 8u;
+    const unsigned grid = a.ntiles < cap ? a.ntiles : cap;
+    const int mode = !e.fast_ok ? 2 : (e.fuse_bias ? 1 : 0);
+    if (mode == 0) stem_tc_kernel<0><<<grid, 128, smem, st>>>(a, e);
+    else if (mode == 1) stem_tc_kernel<1><<<grid, 128, smem, st>>>(a, e);
+    else stem_tc_kernel<2><<<grid, 128, smem, st>>>(a, e);
+    return cudaGetLastError();
 }
 
 // ---- host side ------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtengine_b200.so")
+# TB200_LIB: debug builds of the same library (tools/build_trace_lib.sh); never a different implementation
+LIB_PATH = os.environ.get("TB200_LIB") or os.path.join(_HERE, "libtengine_b200.so")
 _lib = None
 
 

@@ -5,6 +5,7 @@ import os
 import sys
 
 os.environ["TB200_GEMM_TRACE"] = "1"
+os.environ.setdefault("TB200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "trace", "libtengine_b200_trace.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
