@@ -580,6 +580,8 @@ struct StemArgs
     int n, c, h, w_in, oh, ow, ocp, oc, stride, ph, pw;
     unsigned npix, ntiles;
     uint32_t idesc, tmem_cols;
+    int tiles_w, tiles_h, box_w, box_h, in_bytes; // TMA-staged input window (16 x 8 output pixels per tile)
+    int xoff; // the window starts xoff bytes left of the first tap: the innermost TMA coordinate must be 16-byte aligned
 };
 
 template <bool FUSE>
@@ -613,19 +615,28 @@ __device__ __forceinline__ void stem_unit_fast(const uint32_t (&v)[16], uint32_t
 // row r, 16-byte chunk c16 of a SW32 K-major tile (8-row groups of 256 bytes, chunk index ^= bit 2 of the row)
 __device__ __forceinline__ uint32_t sw32_offset(int r, int c16) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 32 + ((c16 ^ ((r >> 2) & 1)) << 4)); }
 
-template <int MODE> // 0 fast, 1 fast + fused bias, 2 exact
-__global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __grid_constant__ EpiParams e)
+// TMA_IN: the input window of the tile (3 channel planes x box_h rows x box_w bytes, zero-filled outside the image) is
+// staged in shared memory by one 4-D TMA load, double-buffered; the gather is then 27 unpredicated LDS.U8 + IMAD per
+// pixel.  Without it (image width not a multiple of 16) every thread gathers from global memory with bounds predicates,
+// which costs more instructions than the whole epilogue.
+template <int MODE, bool TMA_IN> // MODE: 0 fast, 1 fast + fused bias, 2 exact
+__global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemArgs a, const __grid_constant__ EpiParams e)
 {
     extern __shared__ __align__(1024) uint8_t stem_smem[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stem_smem) + 1023) & ~(uintptr_t)1023);
     const uint32_t sA = smem_u32(sm), sB = sA + 4096, sPar = sB + (uint32_t)a.ocp * 32u;
+    const uint32_t in_stride = ((uint32_t)a.in_bytes + 127u) & ~127u;
+    const uint32_t sIn = (sPar + (uint32_t)a.ocp * 8u + 127u) & ~127u;
     __shared__ __align__(8) uint64_t mma_done;
+    __shared__ __align__(8) uint64_t in_full[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tw = tid & 15, th = tid >> 4; // TMA_IN: the tile is 16 x 8 output pixels
 
     if (tid == 0)
     {
         mbar_init(&mma_done, 1);
+        mbar_init(&in_full[0], 1), mbar_init(&in_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0)
@@ -633,6 +644,26 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    __syncthreads();
+    auto tile_coords = [&](unsigned tile, int& n, int& oh0, int& ow0)
+    {
+        const unsigned r = tile / (unsigned)a.tiles_w;
+        ow0 = (int)(tile - r * a.tiles_w) * 16;
+        n = (int)(r / (unsigned)a.tiles_h);
+        oh0 = (int)(r - (unsigned)n * a.tiles_h) * 8;
+    };
+    // (kept in the kernel body: the tensor map must be addressed as the kernel parameter itself, which a lambda that is
+    //  not inlined does not guarantee -- compute-sanitizer: illegal instruction at the cp.async.bulk.tensor)
+#define TB200_STEM_LOAD_TILE(TILE, BUF)                                                                                               \
+    do                                                                                                                                \
+    {                                                                                                                                 \
+        int n_, oh0_, ow0_;                                                                                                           \
+        tile_coords((TILE), n_, oh0_, ow0_);                                                                                          \
+        mbar_expect_tx(&in_full[(BUF)], (uint32_t)a.in_bytes);                                                                        \
+        tma_load_4d(&tmap_in, &in_full[(BUF)], sm + (sIn - sA) + (size_t)(BUF) * in_stride, ow0_ * a.stride - a.pw - a.xoff, oh0_ * a.stride - a.ph, \
+                    0, n_);                                                                                                           \
+    } while (0)
+    if (TMA_IN && tid == 0 && blockIdx.x < a.ntiles) TB200_STEM_LOAD_TILE(blockIdx.x, 0);
     // ---- B tile and the epilogue constants (identical for every CTA; L2 / L1 resident) ----
     for (int i = tid; i < a.ocp * 2; i += 128)
     {
@@ -641,22 +672,23 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
     }
     for (int c = tid; c < a.ocp; c += 128) sts_f2(sPar + c * 8, (MODE != 2) ? __ldg(e.fast_par + c) : make_float2(0.f, 0.f));
 
-    uint32_t phase = 0;
+    uint32_t phase = 0, it = 0;
     uint32_t tmem_base = 0;
-    for (unsigned tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    for (unsigned tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++)
     {
-        // ---- A row of this thread's pixel: gather the 3x3 x C window from the NCHW planes ----
-        const unsigned pix = tile * 128u + (unsigned)tid;
         uint32_t row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (pix < a.npix)
+        unsigned pix;
+        bool valid;
+        if (TMA_IN)
         {
-            const unsigned prow = pix / (unsigned)a.ow;
-            const int ow = (int)(pix - prow * a.ow);
-            const int n = (int)(prow / (unsigned)a.oh);
-            const int oh = (int)(prow - (unsigned)n * a.oh);
-            const int iy0 = oh * a.stride - a.ph, ix0 = ow * a.stride - a.pw;
-            const size_t plane = (size_t)a.h * a.w_in;
-            const uint8_t* img = a.in + (size_t)n * a.c * plane;
+            int n, oh0, ow0;
+            tile_coords(tile, n, oh0, ow0);
+            const int oh = oh0 + th, ow = ow0 + tw;
+            valid = oh < a.oh && ow < a.ow;
+            pix = ((unsigned)n * a.oh + oh) * a.ow + ow;
+            const int buf = it & 1;
+            mbar_wait(&in_full[buf], (it >> 1) & 1);
+            const uint32_t base = sIn + (uint32_t)buf * in_stride + (uint32_t)((th * a.stride) * a.box_w + tw * a.stride + a.xoff);
 #pragma unroll
             for (int c = 0; c < 3; c++)
             {
@@ -664,17 +696,50 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
                 {
 #pragma unroll
                     for (int kh = 0; kh < 3; kh++)
-                    {
-                        const int iy = iy0 + kh;
-                        const bool rok = iy >= 0 && iy < a.h;
-                        const uint8_t* rp = img + (size_t)c * plane + (size_t)(rok ? iy : 0) * a.w_in;
 #pragma unroll
                         for (int kw = 0; kw < 3; kw++)
                         {
-                            const int ix = ix0 + kw;
-                            const uint32_t b = (rok && ix >= 0 && ix < a.w_in) ? (uint32_t)__ldg(rp + ix) : 0u;
+                            uint32_t b;
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(base + (uint32_t)((c * a.box_h + kh) * a.box_w + kw)));
                             const int k = (c * 3 + kh) * 3 + kw; // compile-time after unrolling
-                            row[k >> 2] |= b << (8 * (k & 3));
+                            row[k >> 2] += b << (8 * (k & 3)); // disjoint bytes: add == or (IMAD, off the ALU pipe)
+                        }
+                }
+            }
+        }
+        else
+        {
+            // ---- gather the 3x3 x C window from the NCHW planes in global memory ----
+            pix = tile * 128u + (unsigned)tid;
+            valid = pix < a.npix;
+            if (valid)
+            {
+                const unsigned prow = pix / (unsigned)a.ow;
+                const int ow = (int)(pix - prow * a.ow);
+                const int n = (int)(prow / (unsigned)a.oh);
+                const int oh = (int)(prow - (unsigned)n * a.oh);
+                const int iy0 = oh * a.stride - a.ph, ix0 = ow * a.stride - a.pw;
+                const size_t plane = (size_t)a.h * a.w_in;
+                const uint8_t* img = a.in + (size_t)n * a.c * plane;
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                {
+                    if (c < a.c)
+                    {
+#pragma unroll
+                        for (int kh = 0; kh < 3; kh++)
+                        {
+                            const int iy = iy0 + kh;
+                            const bool rok = iy >= 0 && iy < a.h;
+                            const uint8_t* rp = img + (size_t)c * plane + (size_t)(rok ? iy : 0) * a.w_in;
+#pragma unroll
+                            for (int kw = 0; kw < 3; kw++)
+                            {
+                                const int ix = ix0 + kw;
+                                const uint32_t b = (rok && ix >= 0 && ix < a.w_in) ? (uint32_t)__ldg(rp + ix) : 0u;
+                                const int k = (c * 3 + kh) * 3 + kw;
+                                row[k >> 2] |= b << (8 * (k & 3));
+                            }
                         }
                     }
                 }
@@ -689,6 +754,8 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
         tmem_base = tmem_slot;
         if (tid == 0)
         {
+            // everybody has read this tile's window: prefetch the next one into the other buffer
+            if (TMA_IN && tile + gridDim.x < a.ntiles) TB200_STEM_LOAD_TILE(tile + gridDim.x, (it + 1) & 1);
             umma_i8(tmem_base, make_smem_desc(sA, 32), make_smem_desc(sB, 32), a.idesc, 0u);
             tcgen05_commit(&mma_done);
         }
@@ -716,7 +783,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
             }
             else
                 stem_unit_fast<MODE == 1>(v, sPar + c * 8, c, e, w);
-            if (pix < a.npix) *reinterpret_cast<uint4*>(op + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (valid) *reinterpret_cast<uint4*>(op + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         // the next tile's MMA overwrites the accumulator and its gather overwrites the A tile (the MMA has completed)
         tcgen05_fence_before();
@@ -731,13 +798,33 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const StemArgs a, const __
     }
 }
 
+#undef TB200_STEM_LOAD_TILE
+
 bool stem_tc_supported(const ConvShape& s, const EpiParams& e)
 {
     return !e.is_uint8 && s.kh == 3 && s.kw == 3 && s.c <= 3 && s.group == 1 && s.dh == 1 && s.dw == 1 && s.sh == s.sw && s.ocp <= 256 &&
            (long long)s.n * s.oh * s.ow < (1ll << 31);
 }
 
-cudaError_t launch_stem_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
+// Tensor map over the NCHW network input for the TMA-staged variant: dims (W, H, C, N), box (box_w, box_h, C, 1).
+int stem_plan_create(DwPlan* p, const void* in, const ConvShape& s)
+{
+    p->valid = 0;
+    if (s.w % 16 || getenv("TB200_STEM_NO_TMA")) return -1; // global strides of a tensor map are multiples of 16 bytes
+    // innermost coordinate = ow0*S - pw - xoff must be a multiple of 16 (ow0*S is a multiple of 16*S)
+    const int xoff = (16 - (((-s.pw0) % 16) + 16) % 16) % 16 == 0 ? 0 : ((((-s.pw0) % 16) + 16) % 16);
+    const int box_w = (xoff + (16 - 1) * s.sw + 3 + 15) & ~15, box_h = (8 - 1) * s.sh + 3;
+    if (box_w > 256 || box_h > 256) return -1;
+    const uint64_t dims[4] = {(uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.c, (uint64_t)s.n};
+    const uint64_t strides[3] = {(uint64_t)s.w, (uint64_t)s.w * s.h, (uint64_t)s.w * s.h * s.c};
+    const uint32_t box[4] = {(uint32_t)box_w, (uint32_t)box_h, (uint32_t)s.c, 1u};
+    if (tmap_encode(p->tmap_in, in, 4, dims, strides, box, nullptr, 0)) return -1;
+    p->tile_cols = box_w, p->tile_rows = box_h, p->gpr = xoff;
+    p->valid = 1;
+    return 0;
+}
+
+cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st)
 {
     StemArgs a;
     a.in = (const uint8_t*)in, a.w = (const uint8_t*)w, a.out = (uint8_t*)out;
@@ -747,8 +834,11 @@ cudaError_t launch_stem_tc(const void* in, const void* w, void* out, const ConvS
     uint32_t cols = 32;
     while (cols < (uint32_t)s.ocp) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t smem = 4096 + (size_t)s.ocp * 32 + (size_t)s.ocp * 8 + 1024;
-    a.ntiles = (a.npix + 127u) / 128u;
+    const bool tma = plan.valid != 0;
+    a.tiles_w = (s.ow + 15) / 16, a.tiles_h = (s.oh + 7) / 8;
+    a.box_w = plan.tile_cols, a.box_h = plan.tile_rows, a.in_bytes = tma ? plan.tile_cols * plan.tile_rows * s.c : 0, a.xoff = plan.gpr;
+    a.ntiles = tma ? (unsigned)a.tiles_w * a.tiles_h * s.n : (a.npix + 127u) / 128u;
+    const size_t smem = 4096 + (size_t)s.ocp * 32 + (size_t)s.ocp * 8 + 128 + 2 * (size_t)((a.in_bytes + 127) & ~127) + 1024;
     static int sms = 0;
     if (!sms)
     {
@@ -760,10 +850,18 @@ cudaError_t launch_stem_tc(const void* in, const void* w, void* out, const ConvS
     const unsigned cap = (unsigned)sms * 8u;
     const unsigned grid = a.ntiles < cap ? a.ntiles : cap;
     const int mode = !e.fast_ok ? 2 : (e.fuse_bias ? 1 : 0);
-    if (mode == 0) stem_tc_kernel<0><<<grid, 128, smem, st>>>(a, e);
-    else if (mode == 1) stem_tc_kernel<1><<<grid, 128, smem, st>>>(a, e);
-    else stem_tc_kernel<2><<<grid, 128, smem, st>>>(a, e);
-    return cudaGetLastError();
+    CUtensorMap tm;
+    memcpy(&tm, plan.tmap_in, sizeof tm);
+#define TB200_STEM_CASE(MD, T)                                       \
+    if (mode == MD && tma == T)                                      \
+    {                                                                \
+        stem_tc_kernel<MD, T><<<grid, 128, smem, st>>>(tm, a, e);    \
+        return cudaGetLastError();                                   \
+    }
+    TB200_STEM_CASE(0, true) TB200_STEM_CASE(1, true) TB200_STEM_CASE(2, true)
+    TB200_STEM_CASE(0, false) TB200_STEM_CASE(1, false) TB200_STEM_CASE(2, false)
+#undef TB200_STEM_CASE
+    return cudaErrorInvalidValue;
 }
 
 // ---- host side ------------------------------------------------------------------------------------------

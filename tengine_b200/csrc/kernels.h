@@ -85,7 +85,8 @@ int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b
 int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, void* out, const ConvShape& s, int u8);
 // int8 3x3 stem with C <= 3 on the tensor cores (gemm_tcgen05.cu); weights [OCp][32], k = (c*3 + kh)*3 + kw
 bool stem_tc_supported(const ConvShape& s, const EpiParams& e);
-cudaError_t launch_stem_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+int stem_plan_create(DwPlan* plan, const void* in, const ConvShape& s); // TMA-staged input window; <0: gather from global memory
+cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
 cudaError_t launch_gemm_i8(const GemmPlan& plan, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
 
 } // namespace tb200
