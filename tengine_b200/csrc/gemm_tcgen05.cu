@@ -864,6 +864,152 @@ cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, vo
     return cudaErrorInvalidValue;
 }
 
+// ---- small-K pointwise GEMM: many small CTAs instead of one warp-specialised persistent CTA ---------------------------
+// For K <= 256 (the first pointwise layers: K = 32..128, one or two k-blocks) the persistent kernel above spends more
+// time in hand-overs between its roles than in work (timeline: the epilogue warps idle ~50% of the time).  Here a CTA is
+// four warps = the four TMEM lane quarters; it keeps the N tile's weights in shared memory, double-buffers the A tile
+// (TMA), and per m-tile does: wait A -> one elected thread issues the MMAs -> everybody requantises its own accumulator
+// row and writes its bn contiguous output bytes straight to global memory.  There is no pipelining inside a CTA beyond the
+// A prefetch; 4-8 CTAs are resident per SM (bounded by TMEM columns and shared memory) and overlap each other, the way the
+// tensor-core stem above does (8.2 output bytes/clk/SM vs 4.2 for the persistent kernel on the same layer shape).
+struct SimpleArgs
+{
+    uint8_t* out;
+    long long m;
+    int m_tiles, n_tiles, k_blocks, block_n, block_k, swizzle, ocp, oc, ldo;
+    uint32_t idesc, tmem_cols;
+};
+
+template <int MODE> // 0 fast, 1 fast + fused bias, 2 exact
+__global__ void __launch_bounds__(128) gemm_simple_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                                                           const SimpleArgs g, const __grid_constant__ EpiParams e)
+{
+    extern __shared__ __align__(1024) uint8_t simple_smem[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(simple_smem) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = BLOCK_M * g.block_k, b_bytes = g.block_n * g.block_k, b_al = (b_bytes + 1023) & ~1023u;
+    uint8_t* sA = sm;                                               // [2][k_blocks][a_bytes]
+    uint8_t* sB = sA + 2u * (size_t)g.k_blocks * a_bytes;           // [k_blocks][b_al]
+    const uint32_t sPar = smem_u32(sB) + (uint32_t)g.k_blocks * b_al; // [block_n] x 8 bytes
+    __shared__ __align__(8) uint64_t a_full[2], b_full, mma_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ntile = blockIdx.x % g.n_tiles, n0 = ntile * g.block_n;
+    const int mfirst = blockIdx.x / g.n_tiles, mstep = gridDim.x / g.n_tiles; // the grid is a multiple of n_tiles
+
+    if (tid == 0)
+    {
+        mbar_init(&a_full[0], 1), mbar_init(&a_full[1], 1), mbar_init(&b_full, 1), mbar_init(&mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        mbar_expect_tx(&b_full, (uint32_t)g.k_blocks * b_bytes);
+        for (int kb = 0; kb < g.k_blocks; kb++) tma_load_2d(&tmap_b, &b_full, sB + (size_t)kb * b_al, kb * g.block_k, n0);
+        if (mfirst < g.m_tiles)
+        {
+            mbar_expect_tx(&a_full[0], (uint32_t)g.k_blocks * a_bytes);
+            for (int kb = 0; kb < g.k_blocks; kb++) tma_load_2d(&tmap_a, &a_full[0], sA + (size_t)kb * a_bytes, kb * g.block_k, mfirst * BLOCK_M);
+        }
+    }
+    for (int c = tid; c < g.block_n; c += 128)
+        sts_f2(sPar + c * 8, (MODE != 2 && n0 + c < g.ocp) ? __ldg(e.fast_par + n0 + c) : make_float2(0.f, 0.f));
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+    uint32_t it = 0;
+    for (int mt = mfirst; mt < g.m_tiles; mt += mstep, it++)
+    {
+        const int buf = it & 1;
+        if (tid == 0)
+        {
+            // the other buffer was read by the MMAs of the previous tile, which have completed: prefetch the next tile
+            if (mt + mstep < g.m_tiles)
+            {
+                mbar_expect_tx(&a_full[buf ^ 1], (uint32_t)g.k_blocks * a_bytes);
+                for (int kb = 0; kb < g.k_blocks; kb++)
+                    tma_load_2d(&tmap_a, &a_full[buf ^ 1], sA + ((size_t)(buf ^ 1) * g.k_blocks + kb) * a_bytes, kb * g.block_k, (mt + mstep) * BLOCK_M);
+            }
+            if (it == 0) mbar_wait(&b_full, 0);
+            mbar_wait(&a_full[buf], (it >> 1) & 1);
+            tcgen05_fence_after();
+            for (int kb = 0; kb < g.k_blocks; kb++)
+            {
+                const uint64_t da = make_smem_desc(smem_u32(sA + ((size_t)buf * g.k_blocks + kb) * a_bytes), g.swizzle);
+                const uint64_t db = make_smem_desc(smem_u32(sB + (size_t)kb * b_al), g.swizzle);
+                for (int k = 0; k < g.block_k / 32; k++) umma_i8(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), g.idesc, (kb | k) ? 1u : 0u);
+            }
+            tcgen05_commit(&mma_done);
+        }
+        mbar_wait(&mma_done, it & 1);
+        tcgen05_fence_after();
+
+        // ---- epilogue: lane = output row, 16 channels per TMEM load, straight to global memory ----
+        const long long row = (long long)mt * BLOCK_M + tid;
+        uint8_t* op = g.out + (size_t)(row < g.m ? row : 0) * g.ldo + n0;
+        uint32_t v0[16], v1[16];
+        tmem_ld16(tb, v0);
+        const int nch = g.block_n >> 4;
+        for (int c = 0; c < nch; c += 2)
+        {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld16(tb + (c + 1) * 16, v1);
+            {
+                uint32_t w[4];
+                if (MODE == 2)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        if ((k & 3) == 0) w[k >> 2] = 0;
+                        if (n0 + c * 16 + k < g.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v0[k], n0 + c * 16 + k, e) & 0xffu) << (8 * (k & 3));
+                    }
+                }
+                else
+                    stem_unit_fast<MODE == 1>(v0, sPar + c * 128, n0 + c * 16, e, w);
+                if (row < g.m && n0 + c * 16 < g.ocp) *reinterpret_cast<uint4*>(op + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (c + 1 >= nch) break;
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld16(tb + (c + 2) * 16, v0);
+            {
+                uint32_t w[4];
+                if (MODE == 2)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        if ((k & 3) == 0) w[k >> 2] = 0;
+                        if (n0 + (c + 1) * 16 + k < g.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v1[k], n0 + (c + 1) * 16 + k, e) & 0xffu) << (8 * (k & 3));
+                    }
+                }
+                else
+                    stem_unit_fast<MODE == 1>(v1, sPar + (c + 1) * 128, n0 + (c + 1) * 16, e, w);
+                if (row < g.m && n0 + (c + 1) * 16 < g.ocp) *reinterpret_cast<uint4*>(op + (c + 1) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        // the next tile's MMAs overwrite the accumulator
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0)
+    {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(g.tmem_cols) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1007,7 +1153,24 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
     rc = encode_2d(p->tmap_b, b, (uint64_t)k, (uint64_t)p->n_tiles * p->bnx, (uint64_t)k, p->block_k, p->bnx, p->swizzle);
     if (rc) return rc;
     p->rows_valid = BLOCK_M, p->out_mode = 0;
-    return plan_epilogue(p, out, (uint64_t)m, 1);
+    rc = plan_epilogue(p, out, (uint64_t)m, 1);
+    if (rc) return rc;
+    // small-K layers: the many-small-CTAs kernel (gemm_simple_kernel), N tiles of at most 128 channels
+    p->simple = 0;
+    static const int maxk = getenv("TB200_GEMM_SIMPLE_MAXK") ? atoi(getenv("TB200_GEMM_SIMPLE_MAXK")) : 256;
+    // Opt-in (TB200_GEMM_SIMPLE=1): measured slower than the persistent kernel on every MobileNet-v1 layer it applies to
+    // (batch 256: 148 vs 134 us for K=32/N=64, 84 vs 71 us for K=64/N=128, 72 vs 44 us for K=256/N=256); kept as the
+    // cross-check implementation of the same contraction and for the record of the experiment.
+    if (!u8 && k <= maxk && getenv("TB200_GEMM_SIMPLE"))
+    {
+        const int bn = ocp <= 128 ? ocp : 128;
+        const int a_bytes = BLOCK_M * p->block_k, b_al = (bn * p->block_k + 1023) & ~1023;
+        const int smem = p->k_blocks * (2 * a_bytes + b_al) + bn * 8 + 2048;
+        if (smem <= 112 * 1024 &&
+            encode_2d(p->tmap_b_s, b, (uint64_t)k, (uint64_t)ocp, (uint64_t)k, p->block_k, bn, p->swizzle) == 0)
+            p->simple = 1, p->s_block_n = bn, p->s_n_tiles = (ocp + bn - 1) / bn, p->s_smem = smem, p->out = out;
+    }
+    return 0;
 }
 
 // Implicit-GEMM plan for a dense (group 1, dilation 1) convolution with any kernel size and stride 1 or 2:
@@ -1112,8 +1275,50 @@ static void gemm_trace_report(const GemmPlan& p, const GemmArgs& g, int grid, cu
         }
 }
 
+static cudaError_t launch_gemm_simple(const GemmPlan& p, const EpiParams& e, int num_sms, cudaStream_t st)
+{
+    SimpleArgs g;
+    g.out = (uint8_t*)p.out, g.m = p.m, g.m_tiles = (int)p.m_tiles, g.n_tiles = p.s_n_tiles, g.k_blocks = p.k_blocks, g.block_n = p.s_block_n;
+    g.block_k = p.block_k, g.swizzle = p.swizzle, g.ocp = p.ocp, g.oc = p.oc, g.ldo = p.ldo;
+    g.idesc = make_idesc_i8(p.s_block_n, true, true);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)p.s_block_n) cols <<= 1;
+    g.tmem_cols = cols;
+    int per_sm = (int)(512 / cols);
+    const int by_smem = (220 * 1024) / (p.s_smem + 1024);
+    if (by_smem < per_sm) per_sm = by_smem;
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    long long want = p.m_tiles * p.s_n_tiles, cap = (long long)num_sms * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    grid -= grid % p.s_n_tiles;
+    if (grid < p.s_n_tiles) grid = p.s_n_tiles;
+    CUtensorMap ta, tb;
+    memcpy(&ta, p.tmap_a, sizeof ta);
+    memcpy(&tb, p.tmap_b_s, sizeof tb);
+    const int mode = !e.fast_ok ? 2 : (e.fuse_bias ? 1 : 0);
+    const size_t smem = (size_t)p.s_smem;
+#define TB200_SIMPLE_CASE(MD)                                                                                                  \
+    if (mode == MD)                                                                                                            \
+    {                                                                                                                          \
+        static bool attr = false;                                                                                              \
+        if (!attr)                                                                                                             \
+        {                                                                                                                      \
+            cudaError_t err = cudaFuncSetAttribute(gemm_simple_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024); \
+            if (err != cudaSuccess) return err;                                                                                \
+            attr = true;                                                                                                       \
+        }                                                                                                                      \
+        gemm_simple_kernel<MD><<<grid, 128, smem, st>>>(ta, tb, g, e);                                                         \
+        return cudaGetLastError();                                                                                             \
+    }
+    TB200_SIMPLE_CASE(0) TB200_SIMPLE_CASE(1) TB200_SIMPLE_CASE(2)
+#undef TB200_SIMPLE_CASE
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st)
 {
+    if (p.simple) return launch_gemm_simple(p, e, num_sms, st);
     if (p.block_n <= 0 || p.mt <= 0 || p.stages <= 0 || p.cs <= 0) return cudaErrorInvalidValue; // plan was never created
     GemmArgs g;
     g.m_tiles = (int)p.m_tiles, g.k_blocks = p.k_blocks, g.n_tiles = p.n_tiles, g.block_n = p.block_n;

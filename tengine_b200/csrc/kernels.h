@@ -76,6 +76,10 @@ struct GemmPlan
     int swizzle; // 32 / 64 / 128
     int cs, ngroups, rows_valid, out_mode; // epilogue store groups, see gemm_tcgen05.cu plan_epilogue
     int b_res;                             // weights of the N tile resident in smem (ring carries A only)
+    // small-K variant (gemm_simple_kernel): its own B map (N tiles of <= 128 channels), shared memory per CTA
+    alignas(64) unsigned char tmap_b_s[128];
+    int simple, s_block_n, s_n_tiles, s_smem;
+    void* out;
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
