@@ -883,6 +883,11 @@ int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const*
 {
     if (!g || !host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "bad run arguments");
     int rc;
+    if (!host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "run: null buffer table");
+    for (size_t i = 0; i < g->input_ids.size(); i++)
+        if (!host_inputs[i]) return fail(TB200_ERR_INVALID, "run: input %d has no host buffer", (int)i);
+    for (size_t i = 0; i < g->output_ids.size(); i++)
+        if (!host_outputs[i]) return fail(TB200_ERR_INVALID, "run: output %d has no host buffer (the graph has %d outputs)", (int)i, (int)g->output_ids.size());
     if (g->chunks <= 1 || g->cu_execs.empty())
     {
         for (size_t i = 0; i < g->input_ids.size(); i++)

@@ -7,6 +7,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cmath>
+#include <cstdlib>
+
 namespace tb200 {
 
 // ------------------------------------------------------------------------------------------------------
@@ -449,6 +452,139 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const uint4* __restrict_
     out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
 }
 
+// ---- fast exact variant ---------------------------------------------------------------------------------------------
+// Same guarantee as the convolution epilogue (common.cuh): f is formed with the reference's own operations and roundings,
+// only the final division by s_out is replaced by a multiplication with fl(1/s_out); |t - t_ref| <= 3*2^-24*|t| (+ one more
+// rounding when the uint8 zero point is added inside the round), far inside the 2^-13 tie guard for |t| <= 512.  Elements
+// inside the guard band, vectors that touch pad lanes of a uint8 tensor and parameter sets outside the proven range
+// (launcher) go through the literal code above.  Arithmetic: bytes -> floats without I2FP (PRMT into the mantissa of
+// 1.5*2^23, packed FADD), packed FMUL2/FADD2 chain, integer-domain clamp with one DPX instruction per channel pair.
+template <bool U8>
+__device__ __noinline__ unsigned pointwise_exact_byte(unsigned a, unsigned b, const PointwiseParams& p)
+{
+    float f0, f1;
+    if (U8)
+    {
+        f0 = __fmul_rn((float)((int)a - p.zero0), p.scale0);
+        f1 = __fmul_rn((float)((int)b - p.zero1), p.scale1);
+    }
+    else
+    {
+        f0 = __fmul_rn((float)(int)(int8_t)a, p.scale0);
+        f1 = __fmul_rn((float)(int)(int8_t)b, p.scale1);
+    }
+    float f;
+    if (p.mode == 0) f = (f0 < 0.f) ? ((p.negative_slope == 0.f) ? 0.f : __fmul_rn(f0, p.negative_slope)) : f0;
+    else if (p.mode == 1) f = __fadd_rn(f0, f1);
+    else f = __fmul_rn(f0, f1);
+    if (U8)
+    {
+        if (p.mode == 0) return (unsigned)clamp_u8((int)roundf(__fadd_rn(__fdiv_rn(f, p.out_scale), (float)p.out_zero)));
+        return (unsigned)clamp_u8((int)roundf(__fdiv_rn(f, p.out_scale)) + p.out_zero);
+    }
+    return (unsigned)clamp_i8((int)roundf(__fdiv_rn(f, p.out_scale)));
+}
+
+struct PointwiseFast
+{
+    float r_out;          // fl(1 / s_out)
+    float off0, off1;     // what to subtract from MAGIC + raw byte to get the signed / zero-point-corrected input value
+    uint32_t xor_mask;    // int8: 0x80808080 (bytes become excess-128), uint8: 0
+    uint32_t q_add2, q_max2, q_byte_add; // integer clamp, see common.cuh requant_fast4_i8
+    float zp_in_round;    // uint8 relu: the zero point is added before rounding
+};
+
+template <bool U8, int MODE>
+__global__ void __launch_bounds__(256) pointwise_fast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                                             long long nvec, const PointwiseParams p, const PointwiseFast q)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 va = __ldg(a + i);
+    uint4 vb = make_uint4(0, 0, 0, 0);
+    if (MODE != 0) vb = __ldg(b + i);
+    const unsigned wa[4] = {va.x, va.y, va.z, va.w};
+    const unsigned wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    unsigned wo[4];
+    const int lane0 = (int)((i * 16) % p.cp);
+    if (lane0 + 16 > p.c)
+    {
+        // the vector holds pad lanes: literal path (they must come out as 0)
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+        {
+            unsigned packed = 0;
+            for (int t = 0; t < 4; t++)
+                if (lane0 + w * 4 + t < p.c) packed |= pointwise_exact_byte<U8>((wa[w] >> (8 * t)) & 0xff, (wb[w] >> (8 * t)) & 0xff, p) << (8 * t);
+            wo[w] = packed;
+        }
+        out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        return;
+    }
+    const uint64_t mg = f2_pack(TB200_MAGIC, TB200_MAGIC);
+    const uint64_t o0 = f2_pack(q.off0, q.off0), o1 = f2_pack(q.off1, q.off1);
+    const uint64_t s0 = f2_pack(p.scale0, p.scale0), s1 = f2_pack(p.scale1, p.scale1), rr = f2_pack(q.r_out, q.r_out);
+    const uint64_t sl = f2_pack(p.negative_slope, p.negative_slope), zz = f2_pack(q.zp_in_round, q.zp_in_round);
+    float gmax[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+    {
+        const unsigned xa = wa[w] ^ q.xor_mask, xb = wb[w] ^ q.xor_mask;
+        uint32_t rb[4];
+        float dm = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+            // two bytes -> (MAGIC + byte) bit patterns -> exact floats
+            const uint64_t fa = f2_sub(f2_pack(__uint_as_float(__byte_perm(xa, TB200_MAGIC_BITS, h ? 0x7652 : 0x7650)),
+                                               __uint_as_float(__byte_perm(xa, TB200_MAGIC_BITS, h ? 0x7653 : 0x7651))), o0);
+            uint64_t f = f2_mul(fa, s0);
+            if (MODE != 0)
+            {
+                const uint64_t fb = f2_sub(f2_pack(__uint_as_float(__byte_perm(xb, TB200_MAGIC_BITS, h ? 0x7652 : 0x7650)),
+                                                   __uint_as_float(__byte_perm(xb, TB200_MAGIC_BITS, h ? 0x7653 : 0x7651))), o1);
+                const uint64_t g1 = f2_mul(fb, s1);
+                f = (MODE == 1) ? f2_add(f, g1) : f2_mul(f, g1);
+            }
+            else
+            {
+                // (leaky) relu: max(f0, fl(f0 * slope)) for 0 <= slope < 1 (checked by the launcher)
+                const uint64_t fn = f2_mul(f, sl);
+                float f_lo, f_hi, n_lo, n_hi;
+                f2_unpack(f, f_lo, f_hi);
+                f2_unpack(fn, n_lo, n_hi);
+                f = f2_pack(fmaxf(f_lo, n_lo), fmaxf(f_hi, n_hi));
+            }
+            uint64_t t = f2_mul(f, rr);
+            if (U8 && MODE == 0) t = f2_add(t, zz);
+            const uint64_t r = f2_add(t, mg);
+            const uint64_t d = f2_sub(t, f2_sub(r, mg));
+            float d_lo, d_hi;
+            f2_unpack(d, d_lo, d_hi);
+            dm = fmaxf(dm, fmaxf(fabsf(d_lo), fabsf(d_hi)));
+            f2_unpack_bits(r, rb[2 * h], rb[2 * h + 1]);
+        }
+        gmax[w] = dm;
+        const uint32_t p01 = __viaddmin_s16x2_relu(__byte_perm(rb[0], rb[1], 0x5410), q.q_add2, q.q_max2);
+        const uint32_t p23 = __viaddmin_s16x2_relu(__byte_perm(rb[2], rb[3], 0x5410), q.q_add2, q.q_max2);
+        unsigned word = __byte_perm(p01, p23, 0x6420);
+        if (q.q_byte_add) word = ((word & 0x7f7f7f7fu) + (q.q_byte_add & 0x7f7f7f7fu)) ^ ((word ^ q.q_byte_add) & 0x80808080u);
+        wo[w] = word;
+    }
+    if (fmaxf(fmaxf(gmax[0], gmax[1]), fmaxf(gmax[2], gmax[3])) > 0.5f - TB200_TIE_EPS)
+    {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (gmax[w] > 0.5f - TB200_TIE_EPS)
+            {
+                unsigned packed = 0;
+                for (int t = 0; t < 4; t++) packed |= pointwise_exact_byte<U8>((wa[w] >> (8 * t)) & 0xff, (wb[w] >> (8 * t)) & 0xff, p) << (8 * t);
+                wo[w] = packed;
+            }
+    }
+    out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+}
+
 // concat along channels with per-input requantisation (concat_kernel_ref_int8.c:70-80 roundf(q*s_in/s_out),
 // concat_kernel_ref_uint8.c dequant/requant), and nearest upsample (upsample_ref.c:74); one byte per thread
 // (channel counts such as 255 / 384 need not be multiples of 4 at the seams).
@@ -619,6 +755,42 @@ cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, 
 cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long bytes, const PointwiseParams& p, bool u8, cudaStream_t st)
 {
     const long long nvec = bytes / 16;
+    // ---- fast exact path when the value range is provably inside what its integer clamp / magic rounding can hold ----
+    {
+        const double so = p.out_scale, a0 = fabs((double)p.scale0), a1 = fabs((double)p.scale1);
+        const double in0 = u8 ? 255.0 : 128.0;
+        double tmax = 0;
+        if (p.mode == 0) tmax = in0 * a0 / so;
+        else if (p.mode == 1) tmax = in0 * (a0 + a1) / so;
+        else tmax = in0 * a0 * in0 * a1 / so;
+        const bool slope_ok = p.mode != 0 || (p.negative_slope >= 0.f && p.negative_slope < 1.f);
+        static const bool off = getenv("TB200_POINTWISE_EXACT") != nullptr;
+        if (!off && so > 1e-30 && so < 1e30 && tmax + 256.0 < 32000.0 && slope_ok && p.c >= 16)
+        {
+            PointwiseFast q;
+            q.r_out = 1.0f / p.out_scale;
+            q.xor_mask = u8 ? 0u : 0x80808080u;
+            // as_float(MAGIC_BITS | byte) = MAGIC + byte ; int8 bytes are excess-128 after the xor
+            q.off0 = TB200_MAGIC + (u8 ? (float)p.zero0 : 128.f);
+            q.off1 = TB200_MAGIC + (u8 ? (float)p.zero1 : 128.f);
+            const int q_lo = u8 ? 0 : -127, q_hi = u8 ? 255 : 127;
+            const int zp_after = (u8 && p.mode != 0) ? p.out_zero : 0; // uint8 sum / prod add the zero point after rounding
+            // q' = max(min(q + zp_after - q_lo, q_hi - q_lo), 0), bytes = q' + q_lo
+            const uint32_t add = (uint32_t)(zp_after - q_lo) & 0xffffu, mx = (uint32_t)(q_hi - q_lo) & 0xffffu;
+            q.q_add2 = add | (add << 16), q.q_max2 = mx | (mx << 16);
+            q.q_byte_add = ((uint32_t)q_lo & 0xffu) * 0x01010101u;
+            q.zp_in_round = (u8 && p.mode == 0) ? (float)p.out_zero : 0.f;
+            const unsigned grid = (unsigned)blocks_for(nvec, 256);
+#define TB200_PW_CASE(U, MD)                                                                                                       \
+    if (u8 == U && p.mode == MD)                                                                                                   \
+    {                                                                                                                              \
+        pointwise_fast_kernel<U, MD><<<grid, 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p, q);             \
+        return cudaGetLastError();                                                                                                 \
+    }
+            TB200_PW_CASE(false, 0) TB200_PW_CASE(false, 1) TB200_PW_CASE(false, 2) TB200_PW_CASE(true, 0) TB200_PW_CASE(true, 1) TB200_PW_CASE(true, 2)
+#undef TB200_PW_CASE
+        }
+    }
     if (u8) pointwise_kernel<true><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
     else pointwise_kernel<false><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
     return cudaGetLastError();

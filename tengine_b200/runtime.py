@@ -126,6 +126,7 @@ class Graph:
             assert x.shape == g.dims(t) and x.dtype == g.np_dtype, (x.shape, g.dims(t), x.dtype)
         if outputs is None:
             outputs = [np.empty(g.dims(t), dtype=g.np_dtype) for t in g.outputs]
+        assert len(ins) == len(g.inputs) and len(outputs) == len(g.outputs), "one host buffer per graph input / output"
         ip = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
         op = (C.c_void_p * len(outputs))(*[a.ctypes.data for a in outputs])
         _check(lib().tb200_graph_run(self.h, ip, op))
