@@ -86,6 +86,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, batch, family):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel family, summed over its launches of one step, from the
+    committed `ncu --set full` capture (profiles/r01_ncu_traffic.json; not measured live: ncu replays every kernel ~40x).
+    None when the capture is of another workload / batch."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("workload") != workload or d.get("batch") != batch:
+        return None
+    f = d["families"].get(family)
+    return float(f["dram_bytes_per_step"]) if f else None
+
+
 def build_workload(name, batch):
     from tengine_b200 import abi, workloads
 
@@ -317,7 +331,7 @@ def main():
             "gpu_launches": graph.num_launches() * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "launches_per_step": len(fam[dom]), "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, args.batch, dom), "peak_source": peak_src,
                          "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / float(prof.sum()),
                          "algorithmic_bytes_per_step": dom_bytes},
             "whole_graph": {"algorithmic_gop_per_step": ops / 1e9, "algorithmic_gb_per_step": byts / 1e9,
