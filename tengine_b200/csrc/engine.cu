@@ -50,6 +50,7 @@ enum StepKind
     K_NHWC2NCHW,
     K_CONV_STEM,
     K_STEM_TC,
+    K_GATHER_TC,
     K_CONV_DW,
     K_CONV_DIRECT,
     K_GEMM,
@@ -60,7 +61,7 @@ enum StepKind
     K_UPSAMPLE,
     K_COPY
 };
-static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_stem_nchw_tcgen05", "conv_dw_direct", "conv_direct_dp4a",
+static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_stem_nchw_tcgen05", "conv_gather_tcgen05", "conv_dw_direct", "conv_direct_dp4a",
                                   "gemm_i8_tcgen05", "conv_igemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy"};
 
 struct Step
@@ -82,6 +83,7 @@ struct Step
     // concat / layout
     long long npix = 0;
     int c = 0, cp_in = 0, cp_out = 0, c_off = 0, n = 0, h = 0, w_ = 0, scale = 0;
+    int nhwc16 = 0; // K_GATHER_TC: the input is a 16-channel NHWC tensor (else the NCHW network input)
     float s_in = 0, s_out = 0;
     int z_in = 0, z_out = 0;
     bool u8 = false;
@@ -273,6 +275,7 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_NHWC2NCHW: err = launch_nhwc_to_nchw(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_CONV_STEM: err = launch_conv_stem(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_STEM_TC: err = launch_stem_tc(s.dwp, s.in, s.w, s.out, s.cs, s.epi, st); break;
+    case K_GATHER_TC: err = launch_conv_gather_tc(s.in, s.w, s.out, s.cs, s.epi, s.nhwc16, st); break;
     case K_CONV_DW:
         err = s.dwp.valid ? launch_conv_dw_tma(s.dwp, s.w, s.out, s.cs, s.epi, st) : launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st);
         break;
@@ -383,8 +386,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             if (tin.input_index >= 0 && C <= 3 && L.group == 1 && !u8 && !no_tc && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
                 L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_STEM_TC"))
                 kind[li] = K_STEM_TC, wsize = (size_t)tout.cp * 32; // one 32-byte UMMA k-step per output channel
+            else if (tin.input_index >= 0 && C <= 3 && L.group == 1 && u8 && !no_tc && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
+                     L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_GATHER_TC"))
+                kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 32; // uint8 stem: threads gather, taps outside the image = zero point
             else if (tin.input_index >= 0 && C <= 4 && L.group == 1)
                 kind[li] = K_CONV_STEM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * 4;
+            else if (!no_tc && L.group == 1 && tin.cp == 16 && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 && L.dilation_w == 1 &&
+                     L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_GATHER_TC"))
+                kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 160; // 16-channel input: nine 16-byte taps per pixel, five k-steps
             else if (L.group == C && OC == C && C > 1)
                 kind[li] = K_CONV_DW, wsize = (size_t)L.kernel_h * L.kernel_w * tin.cp;
             else if (!no_tc && L.group == 1 && L.kernel_h == 1 && L.kernel_w == 1 && L.stride_h == 1 && L.stride_w == 1 &&
@@ -449,7 +458,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
-            if (g->tensors[L.inputs[k]].input_index >= 0 && kind[li] != K_CONV_STEM && kind[li] != K_STEM_TC) g->tensors[L.inputs[k]].nhwc_needed = true;
+            if (g->tensors[L.inputs[k]].input_index >= 0 && kind[li] != K_CONV_STEM && kind[li] != K_STEM_TC && !(kind[li] == K_GATHER_TC && g->tensors[L.inputs[k]].d.dims[1] <= 3)) g->tensors[L.inputs[k]].nhwc_needed = true;
     }
     for (int id : g->output_ids)
         if (g->tensors[id].input_index >= 0) g->tensors[id].nhwc_needed = true;
@@ -550,7 +559,14 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     for (int c = 0; c < C; c++)
                         for (int t = 0; t < KH * KW; t++) dst[(size_t)t * tin.cp + c] = src[(size_t)c * KH * KW + t];
                 }
-                else if (kind[li] == K_STEM_TC)
+                else if (kind[li] == K_GATHER_TC && !(tin.input_index >= 0 && C <= 3))
+                {
+                    // 16-channel NHWC input: k = (kh*3 + kw)*16 + c, 160-byte rows (the last 16 bytes stay 0)
+                    for (int o = 0; o < OC; o++)
+                        for (int c = 0; c < C; c++)
+                            for (int t = 0; t < 9; t++) dst[(size_t)o * 160 + t * 16 + c] = src[((size_t)o * C + c) * 9 + t];
+                }
+                else if (kind[li] == K_STEM_TC || kind[li] == K_GATHER_TC)
                 {
                     // [OC][C][3][3] is already k = (c*3 + kh)*3 + kw order: one zero-padded 32-byte row per channel
                     for (int o = 0; o < OC; o++) memcpy(dst + (size_t)o * 32, src + (size_t)o * C * 9, (size_t)C * 9);
@@ -588,6 +604,12 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                         bt[(size_t)t * tout.cp + o] = (int32_t)((int64_t)tin.d.zero_point * (sw - (int64_t)kk * L.weight_zero));
                     }
             }
+            if (kind[li] == K_GATHER_TC && u8)
+            {
+                const int kk = C * L.kernel_h * L.kernel_w;
+                for (int o = 0; o < OC; o++)
+                    for (int k = 0; k < kk; k++) wsum_tot[o] += src[(size_t)o * kk + k];
+            }
             int32_t* b = (int32_t*)(img.data() + blobs[li].bias_off);
             float* sc = (float*)(img.data() + blobs[li].scale_off);
             float* fm = (float*)(img.data() + blobs[li].fast_off); // float2 per channel: (multiplier | bias term, bias bits)
@@ -604,7 +626,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     fm[2 * o] = (o >= OC) ? 0.f : ((L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0]);
                     // tensor-core kinds: corr[oc] = -zx*sum_k w + K*zx*zw (all taps in bounds), carried in the .y lane
                     int32_t corr = 0;
-                    if (tc && o < OC)
+                    if ((tc || kind[li] == K_GATHER_TC) && o < OC)
                     {
                         const int64_t kreal = fc ? (int64_t)C * H * W : (int64_t)C * L.kernel_h * L.kernel_w;
                         corr = (int32_t)(-(int64_t)tin.d.zero_point * wsum_tot[o] + kreal * tin.d.zero_point * L.weight_zero);
@@ -703,7 +725,9 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
                     }
                 }
-                if (s.kind == K_CONV_STEM || s.kind == K_STEM_TC) s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
+                if (s.kind == K_CONV_STEM || s.kind == K_STEM_TC || (s.kind == K_GATHER_TC && tin.input_index >= 0 && C <= 3))
+                    s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
+                s.nhwc16 = (s.kind == K_GATHER_TC && !(tin.input_index >= 0 && C <= 3)) ? 1 : 0;
                 if (s.kind == K_STEM_TC) stem_plan_create(&s.dwp, s.in, s.cs); // falls back to the global-memory gather
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)

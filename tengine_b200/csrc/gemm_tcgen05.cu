@@ -864,6 +864,264 @@ cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, vo
     return cudaErrorInvalidValue;
 }
 
+// ---- gather convolution on the tensor cores (uint8 stems, 3x3 convolutions over 16-channel NHWC tensors) ---------------
+// Same skeleton as the stem above, for the two YOLOv3-tiny layers the implicit GEMM cannot take: the uint8 NCHW stem
+// (3 -> 16 channels at 416x416) and the 3x3 convolution whose input has only 16 channels (a 32-byte UMMA k-step would
+// straddle two filter taps of a 4-D TMA box).  Every thread gathers the K bytes of its output pixel itself -- NCHW: 27 byte
+// loads; NHWC16: nine 16-byte loads, one per tap -- and writes them as one row of `ks` SW32 K-major k-block tiles; `ks`
+// MMAs (K = 32 each) accumulate.  uint8: taps outside the image are filled with the input zero point (they then contribute
+// (zx-zx)(w-zw) = 0, exactly like the reference, which skips them), padding K positions hold 0 in A and B, and the thread
+// sums its own row (dp4a) so that  sum (x-zx)(w-zw) = acc - zw*sum(x) + corr[oc]  needs no ones-row and no border table.
+// Takes the role of im2col + sgemm of conv_hcl_run for these shapes (conv_kernel_x86.c:187-242, 1008-1631).
+struct GatherArgs
+{
+    const uint8_t* in;
+    const uint8_t* w; // [OCp][ks*32]; NCHW: k = (c*3 + kh)*3 + kw ; NHWC16: k = (kh*3 + kw)*16 + c ; zero padded
+    uint8_t* out;
+    int n, c, h, w_in, oh, ow, ocp, oc, stride, ph, pw;
+    unsigned npix, ntiles;
+    uint32_t idesc, tmem_cols;
+    int ks, nhwc16;
+    uint32_t fill; // byte for taps outside the image, replicated x4 (uint8: the input zero point; int8: 0)
+    uint32_t fill16[4]; // NHWC16: the same for a whole 16-channel tap; pad channels (c >= C) stay 0 like in the tensor itself
+};
+
+template <int MODE, bool U8> // MODE: 0 fast, 1 fast + fused bias (int8), 2 exact
+__global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a, const __grid_constant__ EpiParams e)
+{
+    extern __shared__ __align__(1024) uint8_t gat_smem[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gat_smem) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sA = smem_u32(sm), sB = sA + (uint32_t)a.ks * 4096u, b_tile = (uint32_t)a.ocp * 32u, sPar = sB + (uint32_t)a.ks * b_tile;
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0)
+    {
+        mbar_init(&mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // B tiles (one per k-step) and the epilogue constants: identical for every CTA, L2 resident
+    for (int i = tid; i < a.ks * a.ocp * 2; i += 128)
+    {
+        const int kb = i / (a.ocp * 2), j = i - kb * (a.ocp * 2), r = j >> 1, c16 = j & 1;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w + ((size_t)r * a.ks + kb) * 32) + c16);
+        sts_u4(sB + (uint32_t)kb * b_tile + sw32_offset(r, c16), v.x, v.y, v.z, v.w);
+    }
+    for (int c = tid; c < a.ocp; c += 128) sts_f2(sPar + c * 8, (MODE != 2 || U8) ? __ldg(e.fast_par + c) : make_float2(0.f, 0.f));
+
+    uint32_t phase = 0;
+    for (unsigned tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    {
+        const unsigned pix = tile * 128u + (unsigned)tid;
+        const bool valid = pix < a.npix;
+        int32_t sx = 0;
+        int n = 0, oh = 0, ow = 0;
+        if (valid)
+        {
+            const unsigned prow = pix / (unsigned)a.ow;
+            ow = (int)(pix - prow * a.ow);
+            n = (int)(prow / (unsigned)a.oh);
+            oh = (int)(prow - (unsigned)n * a.oh);
+        }
+        const int iy0 = oh * a.stride - a.ph, ix0 = ow * a.stride - a.pw;
+        if (a.nhwc16)
+        {
+            // nine 16-byte taps + one half-row of padding = 160 bytes = five k-steps
+            const uint8_t* img = a.in + (size_t)n * a.h * a.w_in * 16;
+#pragma unroll
+            for (int t = 0; t < 10; t++)
+            {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (t < 9)
+                {
+                    const int iy = iy0 + t / 3, ix = ix0 + t % 3;
+                    v = make_uint4(a.fill16[0], a.fill16[1], a.fill16[2], a.fill16[3]);
+                    if (valid && iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_in) v = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)iy * a.w_in + ix) * 16));
+                    if (U8) sx = (int32_t)__dp4a(v.w, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.x, 0x01010101u, (unsigned)sx))));
+                }
+                sts_u4(sA + (uint32_t)(t >> 1) * 4096u + sw32_offset(tid, t & 1), v.x, v.y, v.z, v.w);
+            }
+        }
+        else
+        {
+            uint32_t row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const size_t plane = (size_t)a.h * a.w_in;
+            const uint8_t* img = a.in + (size_t)n * a.c * plane;
+            const uint32_t fb = a.fill & 0xffu;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+            {
+                if (c < a.c)
+                {
+#pragma unroll
+                    for (int kh = 0; kh < 3; kh++)
+                    {
+                        const int iy = iy0 + kh;
+                        const bool rok = valid && iy >= 0 && iy < a.h;
+                        const uint8_t* rp = img + (size_t)c * plane + (size_t)(rok ? iy : 0) * a.w_in;
+#pragma unroll
+                        for (int kw = 0; kw < 3; kw++)
+                        {
+                            const int ix = ix0 + kw;
+                            const uint32_t b = (rok && ix >= 0 && ix < a.w_in) ? (uint32_t)__ldg(rp + ix) : fb;
+                            const int k = (c * 3 + kh) * 3 + kw; // compile-time after unrolling
+                            row[k >> 2] |= b << (8 * (k & 3));
+                        }
+                    }
+                }
+            }
+            if (U8)
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++) sx = (int32_t)__dp4a(row[j], 0x01010101u, (unsigned)sx);
+            }
+            sts_u4(sA + sw32_offset(tid, 0), row[0], row[1], row[2], row[3]);
+            sts_u4(sA + sw32_offset(tid, 1), row[4], row[5], row[6], row[7]);
+        }
+        fence_proxy_async_smem(); // the MMAs read these generic-proxy writes through the async proxy
+        tcgen05_fence_before();
+        __syncthreads(); // (first iteration: also publishes the TMEM address, the B tiles and the constants)
+        tcgen05_fence_after();
+        const uint32_t tmem_base = tmem_slot;
+        if (tid == 0)
+        {
+            for (int kb = 0; kb < a.ks; kb++)
+                umma_i8(tmem_base, make_smem_desc(sA + (uint32_t)kb * 4096u, 32), make_smem_desc(sB + (uint32_t)kb * b_tile, 32), a.idesc, kb ? 1u : 0u);
+            tcgen05_commit(&mma_done);
+        }
+        mbar_wait(&mma_done, phase);
+        phase ^= 1;
+        tcgen05_fence_after();
+
+        uint8_t* op = a.out + (size_t)pix * a.ocp;
+        const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int32_t rowc = U8 ? -e.w_zero * sx : 0;
+        for (int c = 0; c < a.ocp; c += 16)
+        {
+            uint32_t v[16];
+            tmem_ld16(tb + c, v);
+            tmem_ld_wait();
+            uint32_t w[4];
+            if (U8)
+            {
+                int32_t acc[16];
+                uint32_t bad = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const float4 p01 = lds_f4(sPar + c * 8 + j * 32), p23 = lds_f4(sPar + c * 8 + j * 32 + 16);
+                    // (bias term, corr[oc]) per channel: corr = -zx*sum(w) + K*zx*zw travels in the .y lanes
+                    acc[j * 4 + 0] = (int32_t)v[j * 4 + 0] + rowc + __float_as_int(p01.y), acc[j * 4 + 1] = (int32_t)v[j * 4 + 1] + rowc + __float_as_int(p01.w);
+                    acc[j * 4 + 2] = (int32_t)v[j * 4 + 2] + rowc + __float_as_int(p23.y), acc[j * 4 + 3] = (int32_t)v[j * 4 + 3] + rowc + __float_as_int(p23.w);
+                    if (MODE != 2)
+                    {
+                        const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
+                        const int32_t a4[4] = {acc[j * 4], acc[j * 4 + 1], acc[j * 4 + 2], acc[j * 4 + 3]};
+                        w[j] = requant_fast4_u8(a4, e, m4, bad, 1u << (4 * j));
+                    }
+                }
+                if (MODE == 2)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        if ((k & 3) == 0) w[k >> 2] = 0;
+                        if (c + k < a.oc) w[k >> 2] |= ((uint32_t)requant(acc[k], c + k, e) & 0xffu) << (8 * (k & 3));
+                    }
+                }
+                else
+                {
+                    // pad lanes of uint8 tensors hold 0, not the zero point
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if (c + k >= a.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3))), bad &= ~(1u << k);
+                    if (bad)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, acc[k], c + k, e);
+                    }
+                }
+            }
+            else if (MODE == 2)
+            {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    if ((k & 3) == 0) w[k >> 2] = 0;
+                    if (c + k < a.oc) w[k >> 2] |= ((uint32_t)requant((int32_t)v[k], c + k, e) & 0xffu) << (8 * (k & 3));
+                }
+            }
+            else
+                stem_unit_fast<MODE == 1>(v, sPar + c * 8, c, e, w);
+            if (valid) *reinterpret_cast<uint4*>(op + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        tcgen05_fence_before();
+        __syncthreads(); // the next tile's gather overwrites the A tiles, its MMAs the accumulator
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0)
+    {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, int nhwc16, cudaStream_t st)
+{
+    GatherArgs a;
+    a.in = (const uint8_t*)in, a.w = (const uint8_t*)w, a.out = (uint8_t*)out;
+    a.n = s.n, a.c = s.c, a.h = s.h, a.w_in = s.w, a.oh = s.oh, a.ow = s.ow, a.ocp = s.ocp, a.oc = s.oc, a.stride = s.sh, a.ph = s.ph0, a.pw = s.pw0;
+    a.npix = (unsigned)((long long)s.n * s.oh * s.ow);
+    a.ntiles = (a.npix + 127u) / 128u;
+    a.idesc = make_idesc_i8(s.ocp, !e.is_uint8, !e.is_uint8);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)s.ocp) cols <<= 1;
+    a.tmem_cols = cols;
+    a.ks = nhwc16 ? 5 : 1, a.nhwc16 = nhwc16;
+    a.fill = e.is_uint8 ? ((uint32_t)(e.in_zero & 0xff) * 0x01010101u) : 0u;
+    for (int j = 0; j < 4; j++)
+    {
+        a.fill16[j] = 0;
+        for (int t = 0; t < 4; t++)
+            if (j * 4 + t < s.c) a.fill16[j] |= (a.fill & 0xffu) << (8 * t);
+    }
+    const size_t smem = (size_t)a.ks * 4096 + (size_t)a.ks * s.ocp * 32 + (size_t)s.ocp * 8 + 1024;
+    static int sms = 0;
+    if (!sms)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const unsigned cap = (unsigned)sms * 6u;
+    const unsigned grid = a.ntiles < cap ? a.ntiles : cap;
+    const int mode = !e.fast_ok ? 2 : ((!e.is_uint8 && e.fuse_bias) ? 1 : 0);
+#define TB200_GAT_CASE(MD, U)                                                                                                      \
+    if (mode == MD && (e.is_uint8 != 0) == U)                                                                                      \
+    {                                                                                                                              \
+        static bool attr = false;                                                                                                  \
+        if (!attr)                                                                                                                 \
+        {                                                                                                                          \
+            cudaError_t err = cudaFuncSetAttribute(conv_gather_tc_kernel<MD, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+            if (err != cudaSuccess) return err;                                                                                    \
+            attr = true;                                                                                                           \
+        }                                                                                                                          \
+        conv_gather_tc_kernel<MD, U><<<grid, 128, smem, st>>>(a, e);                                                               \
+        return cudaGetLastError();                                                                                                 \
+    }
+    TB200_GAT_CASE(0, false) TB200_GAT_CASE(1, false) TB200_GAT_CASE(2, false) TB200_GAT_CASE(0, true) TB200_GAT_CASE(2, true)
+#undef TB200_GAT_CASE
+    return cudaErrorInvalidValue;
+}
+
 // ---- small-K pointwise GEMM: many small CTAs instead of one warp-specialised persistent CTA ---------------------------
 // For K <= 256 (the first pointwise layers: K = 32..128, one or two k-blocks) the persistent kernel above spends more
 // time in hand-overs between its roles than in work (timeline: the epilogue warps idle ~50% of the time).  Here a CTA is

@@ -91,6 +91,8 @@ int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, void* o
 bool stem_tc_supported(const ConvShape& s, const EpiParams& e);
 int stem_plan_create(DwPlan* plan, const void* in, const ConvShape& s); // TMA-staged input window; <0: gather from global memory
 cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+// 3x3 convolutions whose K the threads gather themselves (uint8 NCHW stems, 16-channel NHWC inputs), gemm_tcgen05.cu
+cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, int nhwc16, cudaStream_t st);
 cudaError_t launch_gemm_i8(const GemmPlan& plan, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
 
 } // namespace tb200
