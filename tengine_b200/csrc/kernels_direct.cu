@@ -744,17 +744,78 @@ cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const Con
     return cudaGetLastError();
 }
 
+// Max pooling whose output has the input's quantisation (the normal case: YOLO, ResNet): the reference's
+// dequantise -> max -> requantise is then the identity on the winning byte (|fl(fl(k*s)/s) - k| <= 1.5*2^-23*|k| << 1/2 before
+// its round()), so the result is the byte-wise max of the window -- int8: followed by the reference's clamp to -127.
+// Thread = one output pixel x 16 channels.
+template <bool U8>
+__global__ void __launch_bounds__(256) pool_max_same_scale_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolShape p)
+{
+    const int cv = p.cp / 16;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)(p.n * p.oh * p.ow * cv);
+    if (idx >= total) return;
+    const unsigned pix = idx / (unsigned)cv;
+    const int c16 = (int)(idx - pix * cv);
+    const unsigned prow = pix / (unsigned)p.ow;
+    const int pw = (int)(pix - prow * p.ow);
+    const int n = (int)(prow / (unsigned)p.oh);
+    const int ph = (int)(prow - (unsigned)n * p.oh);
+    int h0 = ph * p.sh - p.ph0, h1 = h0 + p.kh, w0 = pw * p.sw - p.pw0, w1 = w0 + p.kw;
+    h0 = h0 > 0 ? h0 : 0, w0 = w0 > 0 ? w0 : 0, h1 = h1 < p.h ? h1 : p.h, w1 = w1 < p.w ? w1 : p.w;
+    uint4 m = U8 ? make_uint4(0, 0, 0, 0) : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    for (int i = h0; i < h1; i++)
+        for (int j = w0; j < w1; j++)
+        {
+            const uint4 v = __ldg(in + (((size_t)n * p.h + i) * p.w + j) * cv + c16);
+            if (U8) m = make_uint4(__vmaxu4(m.x, v.x), __vmaxu4(m.y, v.y), __vmaxu4(m.z, v.z), __vmaxu4(m.w, v.w));
+            else m = make_uint4(__vmaxs4(m.x, v.x), __vmaxs4(m.y, v.y), __vmaxs4(m.z, v.z), __vmaxs4(m.w, v.w));
+        }
+    if (!U8) m = make_uint4(__vmaxs4(m.x, 0x81818181u), __vmaxs4(m.y, 0x81818181u), __vmaxs4(m.z, 0x81818181u), __vmaxs4(m.w, 0x81818181u));
+    out[(size_t)pix * cv + c16] = m;
+}
+
 cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st)
 {
+    if (p.method == TB200_POOL_MAX && p.in_scale == p.out_scale && (!u8 || p.in_zero == p.out_zero) && !getenv("TB200_POOL_EXACT"))
+    {
+        const unsigned tot = (unsigned)(p.n * p.oh * p.ow * (p.cp / 16));
+        if (u8) pool_max_same_scale_kernel<true><<<blocks_for(tot, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, p);
+        else pool_max_same_scale_kernel<false><<<blocks_for(tot, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, p);
+        return cudaGetLastError();
+    }
     const unsigned total = (unsigned)(p.n * p.oh * p.ow * (p.cp / 4));
     if (u8) pool_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     else pool_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     return cudaGetLastError();
 }
 
+// ReLU whose output has the input's quantisation (what the reference's quantisation tool writes, quant_save_graph.cpp:136-200):
+// dequantise -> max(., 0) -> requantise is then max(byte, zero point) (int8: max(byte, 0), and the clamp to -127 cannot trigger).
+template <bool U8>
+__global__ void __launch_bounds__(256) relu_same_scale_kernel(const uint4* __restrict__ a, uint4* __restrict__ out, long long nvec, uint32_t floor4)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 v = __ldg(a + i);
+    // pad lanes of uint8 tensors hold 0 and must stay 0: max(0, zp) would be zp -> keep bytes that are 0... they are only 0 in
+    // pad lanes or where the value really is 0 (< zp), in which case zp is the right answer; the launcher therefore uses this
+    // kernel for uint8 only when the tensor has no pad lanes.
+    if (U8) out[i] = make_uint4(__vmaxu4(v.x, floor4), __vmaxu4(v.y, floor4), __vmaxu4(v.z, floor4), __vmaxu4(v.w, floor4));
+    else out[i] = make_uint4(__vmaxs4(v.x, 0u), __vmaxs4(v.y, 0u), __vmaxs4(v.z, 0u), __vmaxs4(v.w, 0u));
+}
+
 cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long bytes, const PointwiseParams& p, bool u8, cudaStream_t st)
 {
     const long long nvec = bytes / 16;
+    if (p.mode == 0 && p.negative_slope == 0.f && p.scale0 == p.out_scale && (!u8 || (p.zero0 == p.out_zero && p.c == p.cp)) &&
+        !getenv("TB200_POINTWISE_EXACT"))
+    {
+        const unsigned grid = (unsigned)blocks_for(nvec, 256);
+        if (u8) relu_same_scale_kernel<true><<<grid, 256, 0, st>>>((const uint4*)a, (uint4*)out, nvec, (uint32_t)(p.out_zero & 0xff) * 0x01010101u);
+        else relu_same_scale_kernel<false><<<grid, 256, 0, st>>>((const uint4*)a, (uint4*)out, nvec, 0u);
+        return cudaGetLastError();
+    }
     // ---- fast exact path when the value range is provably inside what its integer clamp / magic rounding can hold ----
     {
         const double so = p.out_scale, a0 = fabs((double)p.scale0), a1 = fabs((double)p.scale1);

@@ -22,8 +22,13 @@ class _H:  # handle: tensor id + fp32 calibration activation
 
 
 class QuantBuilder:
-    def __init__(self, data_type, batch, c, h, w, seed=1234, calib_batch=2):
+    def __init__(self, data_type, batch, c, h, w, seed=1234, calib_batch=2, inplace=False):
+        """inplace: give max-pooling and ReLU (slope 0) outputs the quantisation of their input, as the reference's
+        quantisation tool does by default (tools/quantize/quant_tool_int8.cpp:67 `inplace = true`,
+        quant_save_graph.cpp:136-200 passes the scale through Pooling(max) / ReLU / Flatten / Reshape / Clip)."""
         import torch
+
+        self.inplace = inplace
 
         self.torch = torch
         self.g = GraphDef(data_type)
@@ -129,12 +134,18 @@ class QuantBuilder:
             oh, ow = self.g.dims(tid)[2:]
             a = a[:, :, :oh, :ow]
         so, zo = self._act_q(a)
+        if self.inplace and method == abi.POOL_MAX:
+            src = self.g.tensors[x.tid]
+            so, zo = src["scale"], src["zero_point"]
         self.g.tensors[tid]["scale"], self.g.tensors[tid]["zero_point"] = float(so), int(zo)
         return _H(tid, a)
 
     def relu(self, x, negative_slope=0.0):
         a = self.torch.nn.functional.leaky_relu(x.act, negative_slope) if negative_slope else self.torch.relu(x.act)
         so, zo = self._act_q(a)
+        if self.inplace and not negative_slope:
+            src = self.g.tensors[x.tid]
+            so, zo = src["scale"], src["zero_point"]
         return _H(self.g.relu(x.tid, so, zo, negative_slope), a)
 
     def add(self, x, y):
@@ -224,7 +235,7 @@ def resnet50(data_type=abi.DT_UINT8, batch=1, res=224, seed=1234, width=1.0, cla
     """ResNet-50 as in benchmark/models/resnet50_benchmark.tmfile (Caffe layout): 7x7 s2 stem with fused ReLU, 3x3 s2
     max-pool (caffe_flavor 1 -> real pads 0,1,0,1), bottlenecks whose projection / first 1x1 carry the stride, Eltwise-sum
     followed by a STANDALONE ReLU node (each re-quantises), global average pool, FC 2048->1000 (Softmax stays on the CPU)."""
-    b = QuantBuilder(data_type, batch, 3, res, res, seed)
+    b = QuantBuilder(data_type, batch, 3, res, res, seed, inplace=True)  # as the reference's quantisation tool writes its models
     ch = lambda c: max(16, int(c * width))
     x = b.conv(b.input, ch(64), 7, stride=2, pad=3, activation=0)
     x = b.pool(x, abi.POOL_MAX, 3, 2, 0, caffe_flavor=1)
@@ -251,7 +262,7 @@ def yolov3_tiny(data_type=abi.DT_UINT8, batch=1, res=416, seed=1234, width=1.0, 
     by a standalone leaky ReLU (slope 0.1), 2x2 max-pools with caffe_flavor 2 / pad_org 1 (real pads 0,1,0,1; the last one
     has stride 1), a single-input Concat, nearest Upsample x2, a two-input Concat (384 ch) and two 1x1 heads of 255 channels
     followed by Dropout (identity)."""
-    b = QuantBuilder(data_type, batch, 3, res, res, seed)
+    b = QuantBuilder(data_type, batch, 3, res, res, seed, inplace=True)  # as the reference's quantisation tool writes its models
     ch = lambda c: max(8, int(c * width))
 
     def cbl(x, oc, k):
