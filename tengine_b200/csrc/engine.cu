@@ -236,6 +236,16 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
     {
         e.fast_lo = (float)(0 - tout.zero_point), e.fast_hi = (float)(255 - tout.zero_point);
         e.fast_r = 1.0f / so;
+        // integer-domain clip + zero point + saturation (common.cuh requant_fast8_u8): the activation bounds become the integers
+        // the reference's own division and round() give for them; q' = max(min(q + zp - L, H - L), 0), byte = q' + L
+        int q_lo = -30000, q_hi = 30000;
+        if (flo > -inf) q_lo = (int)roundf(flo / so);
+        if (fhi < inf) q_hi = (int)roundf(fhi / so);
+        int Lb = q_lo + tout.zero_point, Hb = q_hi + tout.zero_point;
+        Lb = Lb < 0 ? 0 : (Lb > 255 ? 255 : Lb), Hb = Hb > 255 ? 255 : (Hb < 0 ? 0 : Hb);
+        const uint32_t add = (uint32_t)(tout.zero_point - Lb) & 0xffffu, mx = (uint32_t)(Hb - Lb) & 0xffffu;
+        e.q_add2 = add | (add << 16), e.q_max2 = mx | (mx << 16);
+        e.q_byte_add = ((uint32_t)Lb & 0xffu) * 0x01010101u;
     }
     else
     {
@@ -509,7 +519,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         if (L.op != TB200_OP_CONV && L.op != TB200_OP_FC) continue;
         const TensorInfo& tin = g->tensors[L.inputs[0]];
         const TensorInfo& tout = g->tensors[L.output];
-        if (tin.d.data_type == TB200_DT_UINT8) continue;
+        const bool u8b = tin.d.data_type == TB200_DT_UINT8;
         const int OC = tout.d.dims[1];
         const size_t kk = L.op == TB200_OP_FC ? (size_t)tin.d.dims[1] * tin.d.dims[2] * tin.d.dims[3]
                                               : (size_t)(tin.d.dims[1] / L.group) * L.kernel_h * L.kernel_w;
@@ -517,9 +527,12 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         for (int o = 0; o < OC; o++)
         {
             double sumabs = 0;
-            for (size_t k = 0; k < kk; k++) sumabs += abs((int)wsrc[(size_t)o * kk + k]);
-            const double M = (double)tin.d.scale * (double)L.weight_scales[o] / (double)tout.d.scale;
-            const double bound = (128.0 * sumabs + fabs((double)(L.bias ? L.bias[o] : 0))) * fabs(M);
+            if (u8b)
+                for (size_t k = 0; k < kk; k++) sumabs += abs((int)((const uint8_t*)L.weight)[(size_t)o * kk + k] - L.weight_zero);
+            else
+                for (size_t k = 0; k < kk; k++) sumabs += abs((int)wsrc[(size_t)o * kk + k]);
+            const double M = (double)tin.d.scale * (double)L.weight_scales[u8b ? 0 : o] / (double)tout.d.scale;
+            const double bound = ((u8b ? 255.0 : 128.0) * sumabs + fabs((double)(L.bias ? L.bias[o] : 0))) * fabs(M) + 256.0;
             if (!(bound < 32000.0)) fast_int_ok[li] = 0;
         }
     }
@@ -700,7 +713,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
                 s.btab = (const int32_t*)(g->w_arena + blobs[li].btab_off);
                 s.epi.fuse_bias = fuse_bias[li];
-                if (!u8 && !fast_int_ok[li]) s.epi.fast_ok = 0;
+                if (!fast_int_ok[li]) s.epi.fast_ok = 0;
                 ConvShape& cs = s.cs;
                 cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
                 if (fc)
