@@ -96,6 +96,7 @@ struct GemmArgs
     int out_mode;    // coordinates of the output map: 0 (c, row, 0)  1 (c, pixel in image, image)  2 (c, x, image row)
     int par_all;     // the constants of every channel are resident (loaded once); else reloaded per N tile
     int b_res;       // the N tile's weights (all k-blocks) are loaded once and stay in smem; the ring carries A only
+    int teams;       // the epilogue warps form two teams, one per accumulator stage (see the epilogue)
     const int32_t* btab; // [taps][OCp]: zx * (sum_c w[oc][tap][c] - Cin*zw), the correction a padding tap needs
     unsigned long long* trace; // debug (TB200_GEMM_TRACE): event timeline of CTA 0, see gemm_trace_report
 };
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < g.stages; s++) mbar_init(&ctl->full[s], 1), mbar_init(&ctl->empty[s], 1);
-        for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], EPI_WARPS);
+        for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], g.teams ? EPI_WARPS / 2 : EPI_WARPS);
         mbar_init(&ctl->b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -435,7 +436,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             : CS == 4 ? (uint32_t)((lane >> 1) & 3) << 4
                                       : (CS == 2 ? (uint32_t)((lane >> 2) & 1) << 4 : 0u);
         const uint32_t row_off = (uint32_t)lane * 16u * CS;
-        const int gfirst = CS == 8 ? (sub >> 1) : sub, gstep = CS == 8 ? 2 : 4; // groups are dealt to pairs / warps
+        // Two teams (g.teams): warps with sub 0,1 drain accumulator stage 0, warps with sub 2,3 stage 1, each warp taking every
+        // second group of its stage.  A warp then does twice the work per hand-over, and while one team waits for its stage to be
+        // refilled the other one is computing, instead of all sixteen warps idling through the same bubbles together.
+        const int team = sub >> 1;
+        const int gfirst = CS == 8 ? (sub >> 1) : (g.teams ? (sub & 1) : sub), gstep = (CS == 8 || g.teams) ? 2 : 4;
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); };
         uint32_t ucount = 0; // groups this warp has stored (buffer parity)
         const int par_ch = g.n_tiles * g.block_n;
@@ -452,6 +457,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         uint32_t aphase = 0;
         for (int st = blockIdx.x; st < g.num_super; st += gridDim.x)
         {
+            if (g.teams && as != team)
+            {
+                // the other team's stage
+                if (++as == 2) as = 0, aphase ^= 1;
+                continue;
+            }
             const int msup = st / g.n_tiles;
             const int mt0 = msup * g.mt;
             const int n0 = (st - msup * g.n_tiles) * g.block_n;
@@ -1584,6 +1595,8 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     g.par_all = par_ch <= PAR_MAX ? 1 : 0;
     const int a_bytes = BLOCK_M * p.block_k, b_bytes = (p.bnx * p.block_k + 1023) & ~1023;
     g.b_res = p.b_res;
+    static const int teams_env = getenv("TB200_GEMM_TEAMS") ? atoi(getenv("TB200_GEMM_TEAMS")) : 0;
+    g.teams = (teams_env && p.cs != 8 && p.n_tiles * p.block_n <= PAR_MAX) ? 1 : 0;
     const size_t smem = (size_t)p.stages * (a_bytes + (p.b_res ? 0 : b_bytes)) + (p.b_res ? (size_t)p.k_blocks * b_bytes : 0) +
                         (size_t)EPI_WARPS * 2 * 512 * (p.cs == 8 ? 4 : p.cs) + sizeof(GemmSmemCtl) +
                         (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
