@@ -396,9 +396,10 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             if (tin.input_index >= 0 && C <= 3 && L.group == 1 && !u8 && !no_tc && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
                 L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_STEM_TC"))
                 kind[li] = K_STEM_TC, wsize = (size_t)tout.cp * 32; // one 32-byte UMMA k-step per output channel
-            else if (tin.input_index >= 0 && C <= 3 && L.group == 1 && u8 && !no_tc && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
-                     L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_GATHER_TC"))
-                kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 32; // uint8 stem: threads gather, taps outside the image = zero point
+            else if (tin.input_index >= 0 && C <= 3 && L.group == 1 && !no_tc && L.kernel_h == L.kernel_w && (L.kernel_h == 7 || (u8 && L.kernel_h == 3)) &&
+                     L.dilation_h == 1 && L.dilation_w == 1 && L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_GATHER_TC"))
+                // uint8 3x3 stems and 7x7 stems (ResNet): threads gather, taps outside the image = zero point; K padded to 32*ks
+                kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 32 * ((C * L.kernel_h * L.kernel_w + 31) / 32);
             else if (tin.input_index >= 0 && C <= 4 && L.group == 1)
                 kind[li] = K_CONV_STEM, wsize = (size_t)tout.cp * L.kernel_h * L.kernel_w * 4;
             else if (!no_tc && L.group == 1 && tin.cp == 16 && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 && L.dilation_w == 1 &&
@@ -581,8 +582,9 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 }
                 else if (kind[li] == K_STEM_TC || kind[li] == K_GATHER_TC)
                 {
-                    // [OC][C][3][3] is already k = (c*3 + kh)*3 + kw order: one zero-padded 32-byte row per channel
-                    for (int o = 0; o < OC; o++) memcpy(dst + (size_t)o * 32, src + (size_t)o * C * 9, (size_t)C * 9);
+                    // [OC][C][KH][KW] is already k = (c*KH + kh)*KW + kw order: one zero-padded row of 32*ks bytes per channel
+                    const size_t kk = (size_t)C * KH * KW, kp = ((kk + 31) / 32) * 32;
+                    for (int o = 0; o < OC; o++) memcpy(dst + (size_t)o * kp, src + (size_t)o * kk, kk);
                 }
                 else
                 {

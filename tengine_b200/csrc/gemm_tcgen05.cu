@@ -193,8 +193,8 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
     uint32_t w[4];
     if (!EXACT)
     {
-        // (the packed requant_unit16_u8 of the gather kernel was measured SLOWER here: 8.0 vs 6.7 ms for ResNet-50 uint8's 1x1
-        //  layers -- this kernel sits at its 96-register cap and the extra live values spill)
+        // (the packed requant_unit16_u8 of the gather kernel was measured SLOWER here, with and without the TMEM prefetch:
+        //  8.0 vs 6.7 ms for ResNet-50 uint8's 1x1 layers)
         uint32_t bad = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -899,7 +899,7 @@ struct GatherArgs
     uint32_t fill16[4]; // NHWC16: the same for a whole 16-channel tap; pad channels (c >= C) stay 0 like in the tensor itself
 };
 
-template <int MODE, bool U8> // MODE: 0 fast, 1 fast + fused bias (int8), 2 exact
+template <int MODE, bool U8, int KHW> // MODE: 0 fast, 1 fast + fused bias (int8), 2 exact; KHW: 3 or 7 (NCHW stems; NHWC16 is 3x3)
 __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a, const __grid_constant__ EpiParams e)
 {
     extern __shared__ __align__(1024) uint8_t gat_smem[];
@@ -963,7 +963,11 @@ __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a,
         }
         else
         {
-            uint32_t row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            // NCHW stem: C*KHW*KHW bytes (27 for 3x3, 147 for ResNet's 7x7), k = (c*KHW + kh)*KHW + kw, in NW words = NW/8 k-steps
+            constexpr int NW = KHW == 3 ? 8 : 40;
+            uint32_t row[NW];
+#pragma unroll
+            for (int j = 0; j < NW; j++) row[j] = 0;
             const size_t plane = (size_t)a.h * a.w_in;
             const uint8_t* img = a.in + (size_t)n * a.c * plane;
             const uint32_t fb = a.fill & 0xffu;
@@ -973,17 +977,17 @@ __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a,
                 if (c < a.c)
                 {
 #pragma unroll
-                    for (int kh = 0; kh < 3; kh++)
+                    for (int kh = 0; kh < KHW; kh++)
                     {
                         const int iy = iy0 + kh;
                         const bool rok = valid && iy >= 0 && iy < a.h;
                         const uint8_t* rp = img + (size_t)c * plane + (size_t)(rok ? iy : 0) * a.w_in;
 #pragma unroll
-                        for (int kw = 0; kw < 3; kw++)
+                        for (int kw = 0; kw < KHW; kw++)
                         {
                             const int ix = ix0 + kw;
                             const uint32_t b = (rok && ix >= 0 && ix < a.w_in) ? (uint32_t)__ldg(rp + ix) : fb;
-                            const int k = (c * 3 + kh) * 3 + kw; // compile-time after unrolling
+                            const int k = (c * KHW + kh) * KHW + kw; // compile-time after unrolling
                             row[k >> 2] |= b << (8 * (k & 3));
                         }
                     }
@@ -992,10 +996,11 @@ __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a,
             if (U8)
             {
 #pragma unroll
-                for (int j = 0; j < 8; j++) sx = (int32_t)__dp4a(row[j], 0x01010101u, (unsigned)sx);
+                for (int j = 0; j < NW; j++) sx = (int32_t)__dp4a(row[j], 0x01010101u, (unsigned)sx);
             }
-            sts_u4(sA + sw32_offset(tid, 0), row[0], row[1], row[2], row[3]);
-            sts_u4(sA + sw32_offset(tid, 1), row[4], row[5], row[6], row[7]);
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                sts_u4(sA + (uint32_t)(j >> 1) * 4096u + sw32_offset(tid, j & 1), row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]);
         }
         fence_proxy_async_smem(); // the MMAs read these generic-proxy writes through the async proxy
         tcgen05_fence_before();
@@ -1073,6 +1078,7 @@ __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a,
 
 cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, int nhwc16, cudaStream_t st)
 {
+    const int khw = nhwc16 ? 3 : s.kh;
     GatherArgs a;
     a.in = (const uint8_t*)in, a.w = (const uint8_t*)w, a.out = (uint8_t*)out;
     a.n = s.n, a.c = s.c, a.h = s.h, a.w_in = s.w, a.oh = s.oh, a.ow = s.ow, a.ocp = s.ocp, a.oc = s.oc, a.stride = s.sh, a.ph = s.ph0, a.pw = s.pw0;
@@ -1082,7 +1088,7 @@ cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, cons
     uint32_t cols = 32;
     while (cols < (uint32_t)s.ocp) cols <<= 1;
     a.tmem_cols = cols;
-    a.ks = nhwc16 ? 5 : 1, a.nhwc16 = nhwc16;
+    a.ks = nhwc16 ? 5 : (s.c * s.kh * s.kw + 31) / 32, a.nhwc16 = nhwc16;
     a.fill = e.is_uint8 ? ((uint32_t)(e.in_zero & 0xff) * 0x01010101u) : 0u;
     for (int j = 0; j < 4; j++)
     {
@@ -1101,20 +1107,21 @@ cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, cons
     const unsigned cap = (unsigned)sms * 6u;
     const unsigned grid = a.ntiles < cap ? a.ntiles : cap;
     const int mode = !e.fast_ok ? 2 : ((!e.is_uint8 && e.fuse_bias) ? 1 : 0);
-#define TB200_GAT_CASE(MD, U)                                                                                                      \
-    if (mode == MD && (e.is_uint8 != 0) == U)                                                                                      \
+#define TB200_GAT_CASE(MD, U, K)                                                                                                   \
+    if (mode == MD && (e.is_uint8 != 0) == U && khw == K)                                                                          \
     {                                                                                                                              \
         static bool attr = false;                                                                                                  \
         if (!attr)                                                                                                                 \
         {                                                                                                                          \
-            cudaError_t err = cudaFuncSetAttribute(conv_gather_tc_kernel<MD, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+            cudaError_t err = cudaFuncSetAttribute(conv_gather_tc_kernel<MD, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
             if (err != cudaSuccess) return err;                                                                                    \
             attr = true;                                                                                                           \
         }                                                                                                                          \
-        conv_gather_tc_kernel<MD, U><<<grid, 128, smem, st>>>(a, e);                                                               \
+        conv_gather_tc_kernel<MD, U, K><<<grid, 128, smem, st>>>(a, e);                                                            \
         return cudaGetLastError();                                                                                                 \
     }
-    TB200_GAT_CASE(0, false) TB200_GAT_CASE(1, false) TB200_GAT_CASE(2, false) TB200_GAT_CASE(0, true) TB200_GAT_CASE(2, true)
+    TB200_GAT_CASE(0, false, 3) TB200_GAT_CASE(1, false, 3) TB200_GAT_CASE(2, false, 3) TB200_GAT_CASE(0, true, 3) TB200_GAT_CASE(2, true, 3)
+    TB200_GAT_CASE(0, false, 7) TB200_GAT_CASE(1, false, 7) TB200_GAT_CASE(2, false, 7) TB200_GAT_CASE(0, true, 7) TB200_GAT_CASE(2, true, 7)
 #undef TB200_GAT_CASE
     return cudaErrorInvalidValue;
 }
