@@ -39,8 +39,12 @@ def main(rep, out=None):
             u = units[ix[m]] if m in ix else ""
             try:
                 f = float(v.replace(",", ""))
-                if u == "ns":
+                if u in ("ns", "nsecond"):
                     f /= 1000.0
+                if u in ("ms", "msecond") and m == "gpu__time_duration.sum":
+                    f *= 1000.0
+                if u in ("s", "second") and m == "gpu__time_duration.sum":
+                    f *= 1e6
                 if u in ("Mbyte", "MB"):
                     f *= 1e6
                 if u in ("Kbyte", "KB"):
