@@ -73,3 +73,28 @@ def layer_outputs(g):
 def diff_stats(a, b):
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     return int(d.max()), int((d > 0).sum())
+
+
+def single_layer_graph(g, li):
+    """Layer `li` of GraphDef `g` as a graph of its own (its input tensors become graph inputs).  Returns the new graph and the
+    ids (in `g`) of the tensors to feed.  Used to compare uint8 layers one at a time: the reference simulates uint8 in fp32, so
+    each layer may differ by 1 LSB and over a deep network those differences propagate."""
+    from tengine_b200.graphdef import GraphDef
+
+    L = g.layers[li]
+    h = GraphDef(g.data_type)
+    ids = {}
+    for t in L["inputs"]:
+        if t not in ids:
+            src = g.tensors[t]
+            h.tensors.append(dict(dims=src["dims"], scale=src["scale"], zero_point=src["zero_point"]))
+            ids[t] = len(h.tensors) - 1
+            h.inputs.append(ids[t])
+    src = g.tensors[L["output"]]
+    h.tensors.append(dict(dims=src["dims"], scale=src["scale"], zero_point=src["zero_point"]))
+    M = dict(L)
+    M["inputs"] = [ids[t] for t in L["inputs"]]
+    M["output"] = len(h.tensors) - 1
+    h.layers.append(M)
+    h.outputs = [M["output"]]
+    return h, list(ids.keys())

@@ -115,3 +115,33 @@ def test_mobilenet_v1_int8_batch1_bit_exact(oracle, reference):
     for li, L in enumerate(g.layers):
         assert np.array_equal(got[L["output"]], want[L["output"]]), f"layer {li}"
     assert len(np.unique(want[g.outputs[0]])) > 50, "test vacuous: classifier output collapsed"
+
+
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+@pytest.mark.parametrize("net", ["resnet50", "yolov3_tiny"])
+def test_benchmark_graphs_with_inplace_scales(oracle, reference, net, dtype):
+    """C3 / C4 of BASELINE.json at reduced width, quantised the way the reference's own tool does (max pooling and ReLU outputs
+    share the input's scale, tools/quantize/quant_save_graph.cpp:136-200): every layer of the oracle against the UNMODIFIED
+    reference.  This is what the device's byte-wise same-scale pooling / ReLU kernels and the gather-convolution kernels are
+    ultimately compared with (tests/test_gpu_parity.py checks device == oracle on the same graphs)."""
+    if net == "resnet50":
+        g, b = workloads.resnet50(dtype, batch=1, res=96, width=0.25, classes=40, seed=5)
+    else:
+        g, b = workloads.yolov3_tiny(dtype, batch=1, res=96, width=0.25, head=27, seed=6)
+    x = b.random_input(3)
+    want, _ = reference.run(g, [x], want=layer_outputs(g))
+    if dtype == abi.DT_INT8:
+        got = oracle.run(g, [x])
+        for li, L in enumerate(g.layers):
+            assert np.array_equal(got[L["output"]], want[L["output"]]), f"{net} layer {li} {abi.OP_NAMES[L['op']]}"
+        return
+    # uint8: layer by layer on the reference's own tensors (1 LSB per layer is the reference's fp32 noise; over 50+ layers it
+    # propagates to ~10 LSB, which says nothing about any single layer)
+    from tests.helpers import single_layer_graph
+
+    want[g.inputs[0]] = x
+    for li, L in enumerate(g.layers):
+        h, src = single_layer_graph(g, li)
+        got = oracle.run(h, [want[t] for t in src])
+        d = np.abs(got[h.outputs[0]].astype(np.int32) - want[L["output"]].astype(np.int32))
+        assert d.max() <= 1, f"{net} layer {li} {abi.OP_NAMES[L['op']]}: {int(d.max())} LSB"
