@@ -38,6 +38,12 @@ def main():
         # exercises the reference's HCL selections (conv_hcl 1x1, conv_dw_hcl, conv_direct_hcl_int8 3x3)
         g, b = workloads.mobilenet_v1(dt, batch=1, res=64, seed=11, width=0.25, classes=32)
         save(f"ref_mobilenet025_{tag}", g, b.random_input(5), ref)
+    # ResNet-50 / YOLOv3-tiny at reduced width (BASELINE.json C3 / C4 structure), int8, batch 1, quantised with the in-place scales of
+    # the reference's tool: 7x7 stem, bottlenecks with eltwise + standalone ReLU, max pooling, leaky ReLU, concat, upsample
+    g, b = workloads.resnet50(abi.DT_INT8, batch=1, res=96, width=0.25, classes=40, seed=5)
+    save("ref_resnet50_small_int8", g, b.random_input(3), ref)
+    g, b = workloads.yolov3_tiny(abi.DT_INT8, batch=1, res=96, width=0.25, head=27, seed=6)
+    save("ref_yolov3_tiny_small_int8", g, b.random_input(3), ref)
 
 
 if __name__ == "__main__":

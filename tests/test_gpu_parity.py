@@ -49,6 +49,18 @@ def test_int8_bit_exact_vs_reference_fixture(ctx, name, flags):
         assert any("tcgen05" in k for k in kernels), kernels
 
 
+@pytest.mark.parametrize("name", ["ref_resnet50_small_int8", "ref_yolov3_tiny_small_int8"])
+def test_int8_benchmark_graphs_vs_reference_fixture(ctx, name):
+    """Reduced ResNet-50 / YOLOv3-tiny (7x7 stem on the gather kernel, implicit GEMMs, same-scale max pooling and ReLU as byte
+    operations, leaky ReLU, eltwise, concat, upsample): every layer equals the bytes the UNMODIFIED reference produced."""
+    g, x, ref = load_golden(name)
+    outs, tensors, kernels = _run_all_layers(ctx, g, x, abi.PRERUN_DEFAULT)
+    for li, L in enumerate(g.layers):
+        t = L["output"]
+        assert np.array_equal(tensors[t], ref[t]), f"{name}: layer {li} ({kernels[li]}) differs from the reference"
+    assert any("tcgen05" in k for k in kernels), kernels
+
+
 @pytest.mark.parametrize("name", ["ref_tiny_uint8", "ref_mobilenet025_uint8"])
 def test_uint8_vs_reference_fixture(ctx, oracle, name):
     g, x, ref = load_golden(name)

@@ -15,7 +15,7 @@ def test_oracle_reproduces_reference_kats(oracle, kat):
         assert np.abs(real - expected).max() <= tol + 1e-6, (name, mode, real.ravel(), expected.ravel())
 
 
-@pytest.mark.parametrize("name", ["ref_tiny_int8", "ref_mobilenet025_int8"])
+@pytest.mark.parametrize("name", ["ref_tiny_int8", "ref_mobilenet025_int8", "ref_resnet50_small_int8", "ref_yolov3_tiny_small_int8"])
 def test_oracle_bit_exact_vs_reference_fixture_int8(oracle, name):
     g, x, ref = load_golden(name)
     out = oracle.run(g, [x])
