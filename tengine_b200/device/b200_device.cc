@@ -97,7 +97,7 @@ int conv_recipe(const struct conv_param* p, const struct tensor* in, const struc
     if (p->group == 1) return TB200_RECIPE_HCL; // conv_hcl_x86 / conv_direct_hcl_int8_x86
     if (depthwise && in->data_type == TENGINE_DT_INT8 && in->dims[0] == 1 && p->kernel_h == 3 && p->kernel_w == 3 &&
         p->stride_h == p->stride_w && (p->stride_h == 1 || p->stride_h == 2) && p->dilation_h == 1 && p->dilation_w == 1 &&
-        p->pad_h0 == p->pad_h1 && p->pad_w0 == p->pad_w1 && p->pad_h0 == p->pad_w0)
+        p->pad_h0 == p->pad_h1 && p->pad_w0 == p->pad_w1)
         return TB200_RECIPE_HCL; // conv_dw_hcl_x86.c:508-543
     return TB200_RECIPE_REF;     // conv_ref.c
 }

@@ -86,7 +86,7 @@ def test_tiny_net_every_layer_vs_oracle(ctx, oracle, dtype, flags):
         assert np.array_equal(tensors[t], want[t]), f"layer {li} {abi.OP_NAMES[L['op']]} ({kernels[li]})"
 
 
-def _one_conv(rng, dtype, n, c, h, w, oc, k, s, p, group, act, recipe, bias=True):
+def _one_conv(rng, dtype, n, c, h, w, oc, k, s, p, group, act, recipe, bias=True, dilation=1):
     g = GraphDef(dtype)
     u8 = dtype == abi.DT_UINT8
     x = g.input(n, c, h, w, 0.02, 131 if u8 else 0)
@@ -98,7 +98,8 @@ def _one_conv(rng, dtype, n, c, h, w, oc, k, s, p, group, act, recipe, bias=True
         wq, ws, wz = rng.integers(-127, 128, (oc, c // group, k, k)).astype(np.int8), rng.uniform(0.001, 0.01, oc), 0
         so = 0.02 * 0.0055 * np.sqrt(kk) * 73 * 73 / 100
     b = rng.integers(-2000, 2000, oc).astype(np.int32) if bias else None
-    y = g.conv(x, wq, b, ws, so, 110 if u8 else 0, stride=s, pad=p, group=group, activation=act, recipe=recipe, weight_zero=wz)
+    y = g.conv(x, wq, b, ws, so, 110 if u8 else 0, stride=s, pad=p, dilation=dilation, group=group, activation=act, recipe=recipe,
+               weight_zero=wz)
     g.mark_output(y)
     xin = rng.integers(0, 256, (n, c, h, w)).astype(np.uint8) if u8 else rng.integers(-127, 128, (n, c, h, w)).astype(np.int8)
     return g, xin
@@ -170,6 +171,27 @@ def test_conv_kernels_bit_exact(ctx, oracle, dtype, case):
         assert np.array_equal(got, want), (kern, act, recipe)
 
 
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+@pytest.mark.parametrize("case", [(2, 32, 15, 15, 48, 3, 1, 2, 1, 2), (1, 16, 17, 17, 24, 3, 2, 3, 1, 3), (2, 64, 12, 12, 64, 3, 1, 2, 64, 2),
+                                  (1, 8, 11, 11, 16, 3, 1, 2, 2, 2)],
+                         ids=["dil2", "dil3_s2", "depthwise_dil2", "grouped_dil2"])
+def test_dilated_conv_bit_exact(ctx, oracle, dtype, case):
+    """dilation > 1 (conv_kernel_ref_int8.c:104-121 tap addressing): the general direct kernel, dense / depthwise / grouped."""
+    from tengine_b200 import runtime as rt
+
+    n, c, h, w, oc, k, s, p, group, dil = case
+    rng = np.random.default_rng(sum(case) + dtype)
+    g, x = _one_conv(rng, dtype, n, c, h, w, oc, k, s, p, group, 0, abi.RECIPE_REF, dilation=dil)
+    gr = rt.Graph(ctx, g)
+    try:
+        got = gr.run([x])[0]
+        kern = gr.layer_kernels()[0]
+    finally:
+        gr.close()
+    want = oracle.run(g, [x], uint8_mode=0)[g.outputs[0]]
+    assert np.array_equal(got, want), kern
+
+
 def test_empty_and_bad_inputs_fail_cleanly(ctx):
     from tengine_b200 import runtime as rt
 
@@ -229,6 +251,51 @@ def test_reference_benchmark_graphs_every_layer(ctx, oracle, net, dtype):
     want = oracle.run(g, [x], uint8_mode=0)
     for li, L in enumerate(g.layers):
         assert np.array_equal(tensors[L["output"]], want[L["output"]]), f"{net} layer {li} {abi.OP_NAMES[L['op']]} ({kernels[li]})"
+
+
+FULL = [("resnet50", abi.DT_UINT8, 3), ("resnet50", abi.DT_INT8, 2), ("yolov3_tiny", abi.DT_UINT8, 2), ("yolov3_tiny", abi.DT_INT8, 2)]
+
+
+@pytest.mark.parametrize("net,dtype,batch", FULL, ids=lambda v: str(v))
+def test_full_size_benchmark_graphs_every_layer(ctx, oracle, net, dtype, batch):
+    """C3 (ResNet-50 224x224) and C4 (YOLOv3-tiny 416x416) of BASELINE.json at their REAL width and resolution -- K up to 4608,
+    OC up to 2048, several N tiles with non-resident weights, the 16-bit clamp-range proof deciding MODE per layer -- at a batch
+    the CPU oracle finishes in seconds: every layer bit-exact (uint8: against the exact-integer oracle)."""
+    g, b = getattr(workloads, net)(dtype, batch=batch)
+    x = b.random_input(3)
+    outs, tensors, kernels = _run_all_layers(ctx, g, x, abi.PRERUN_DEFAULT)
+    want = oracle.run(g, [x], uint8_mode=0)
+    for li, L in enumerate(g.layers):
+        assert np.array_equal(tensors[L["output"]], want[L["output"]]), f"{net} layer {li} {abi.OP_NAMES[L['op']]} ({kernels[li]})"
+    for o, t in zip(outs, g.outputs):
+        assert np.array_equal(o, want[t])
+        assert len(np.unique(o)) > 20
+    assert sum("tcgen05" in k for k in kernels) >= (13 if net == "yolov3_tiny" else 54)
+
+
+@pytest.mark.parametrize("net,dtype,batch", [("resnet50", abi.DT_UINT8, 128), ("yolov3_tiny", abi.DT_UINT8, 128)], ids=lambda v: str(v))
+def test_full_size_batch_independence(ctx, oracle, net, dtype, batch):
+    """At the real batch the CPU oracle is too slow; images are independent units, so every image of the big batch must equal
+    the same image run in a small batch that the previous test pins to the oracle (captured CUDA graph, pipelined run)."""
+    from tengine_b200 import runtime as rt
+
+    g, b = getattr(workloads, net)(dtype, batch=batch)
+    x = b.random_input(9)
+    gr = rt.Graph(ctx, g)
+    big = gr.run([x])
+    gr.close()
+    g2, _ = getattr(workloads, net)(dtype, batch=2)
+    gr = rt.Graph(ctx, g2)
+    try:
+        for i in (0, batch // 2 - 1, batch - 2):
+            small = gr.run([x[i:i + 2]])
+            for o_big, o_small in zip(big, small):
+                assert np.array_equal(o_big[i:i + 2], o_small), f"{net}: images {i},{i + 1} differ between batch {batch} and batch 2"
+    finally:
+        gr.close()
+    want = oracle.run(g2, [x[:2]], uint8_mode=0)
+    for o_big, t in zip(big, g2.outputs):
+        assert np.array_equal(o_big[:2], want[t])
 
 
 def test_pipelined_run_equals_unpipelined(ctx):

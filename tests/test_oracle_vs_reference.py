@@ -53,6 +53,20 @@ def test_int8_conv_bit_exact_and_recipe(oracle, reference, case):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("stride", [1, 2])
+def test_int8_depthwise_pad_h_differs_from_pad_w_uses_the_hcl_recipe(oracle, reference, stride):
+    """conv_dw_hcl_x86.c:539 only asks pad_h0 == pad_h1 and pad_w0 == pad_w1; pad_h may differ from pad_w (the kernel pads each
+    axis with its own value, :131-132).  The device glue's conv_recipe() mirrors exactly this predicate."""
+    rng = np.random.default_rng(77 + stride)
+    gd, xin = _rand_conv(rng, abi.DT_INT8, 1, 32, 15, 17, 32, 3, stride, (1, 1, 0, 0), 32, 0, abi.RECIPE_HCL)
+    want, _ = reference.run(gd, [xin])
+    ref = want[gd.outputs[0]]
+    assert np.array_equal(oracle.run(gd, [xin])[gd.outputs[0]], ref)
+    gd.layers[0]["recipe"] = abi.RECIPE_REF  # the other recipe is NOT what the reference computes here (rare 1-LSB cases)
+    other = oracle.run(gd, [xin])[gd.outputs[0]]
+    assert np.abs(other.astype(int) - ref.astype(int)).max() <= 1
+
+
 def test_int8_batched_3x3_reference_bug_is_known(oracle, reference):
     """conv3x3s1_int8_sse ignores the batch dimension (conv_direct_hcl_int8_x86.c:95-200) but wins the
     selection for every int8 3x3 conv; images n>0 are therefore NOT computed by the reference's default path.  The
