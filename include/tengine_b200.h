@@ -34,7 +34,7 @@ extern "C" {
 #define TB200_API
 #endif
 
-#define TB200_ABI_VERSION 1
+#define TB200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------------- */
 #define TB200_OK 0
@@ -60,7 +60,12 @@ enum tb200_op
     TB200_OP_ELTWISE = 4,  /* OP_ELTWISE  eltwise_param (operator/prototype/eltwise_param.h:50-57)   */
     TB200_OP_CONCAT = 5,   /* OP_CONCAT   concat_param (axis == 1 only)                              */
     TB200_OP_UPSAMPLE = 6, /* OP_UPSAMPLE upsample_param (nearest, integer scale)                    */
-    TB200_OP_IDENTITY = 7, /* OP_DROPOUT / OP_FLATTEN / OP_RESHAPE at inference                      */
+    TB200_OP_IDENTITY = 7, /* OP_DROPOUT at inference                                                */
+    TB200_OP_SOFTMAX = 8,  /* OP_SOFTMAX  softmax_param (axis == 1), softmax/softmax_kernel_ref_{int8,uint8}.c */
+    TB200_OP_SIGMOID = 9,  /* OP_SIGMOID  sigmoid/sigmoid_ref.c:84 (int8), :129 (uint8)               */
+    TB200_OP_HARDSWISH = 10, /* OP_HARDSWISH hardswish/hardswish_kernel_ref_uint8.c:41 (uint8 only, as the reference) */
+    TB200_OP_RESHAPE = 11, /* OP_RESHAPE / OP_FLATTEN: the same bytes in NCHW order under the output tensor's dims
+                              (flatten/flatten_ref.c:49-83, reshape/reshape_ref.c)                     */
     TB200_OP_COUNT_
 };
 
@@ -130,7 +135,7 @@ typedef struct tb200_layer_desc
     float bias_scale;
 } tb200_layer_desc;
 
-typedef struct tb200_context tb200_context; /* one per GPU: stream, arenas, device properties */
+typedef struct tb200_context tb200_context; /* one GPU -- or a group of GPUs driven by this process -- : streams, NCCL communicators */
 typedef struct tb200_graph tb200_graph;     /* one per Tengine subgraph (subgraph->device_graph) */
 
 /* ---- library / device ---------------------------------------------------------------------------- */
@@ -145,7 +150,30 @@ TB200_API int tb200_context_destroy(tb200_context* ctx);
 /* the CUDA stream (cudaStream_t) all work of this context is ordered on, for callers that time with events */
 TB200_API void* tb200_context_stream(tb200_context* ctx);
 
-/* pinned host staging memory (what `run` uses internally when the caller's buffer is pageable) */
+/* Several GPUs behind ONE device (the option-blob precedent is trt_option,
+ * source/device/tensorrt/trt_define.h:36-42).  Every tb200_graph_* call on such a context shards dim 0 of the batch
+ * contiguously over the GPUs: prerun plans one shard per GPU, packs the weights once (GPU 0) and moves the arena to
+ * the others with ONE grouped ncclBroadcast (communicators from ncclCommInitAll; NCCL is dlopen'ed); run copies each
+ * GPU's slice of the caller's NCHW buffers straight to that GPU and joins all streams before it returns.  There is no
+ * collective in the steady state.  Listing a device twice (single-GPU test boxes) keeps every mechanism except NCCL
+ * itself, which refuses duplicate devices: the arena is then copied with cudaMemcpyPeerAsync. */
+TB200_API int tb200_context_create_multi(const int* cuda_devices, int num_devices, tb200_context** out);
+TB200_API int tb200_context_num_gpus(tb200_context* ctx);
+TB200_API int tb200_context_gpu(tb200_context* ctx, int index);        /* CUDA ordinal of GPU `index` of the group */
+TB200_API void* tb200_context_stream_of(tb200_context* ctx, int index); /* its stream (cudaStream_t) */
+TB200_API const char* tb200_context_broadcast_kind(tb200_context* ctx); /* "none" | "nccl" | "memcpy_peer" */
+
+/* What set_context_device(ctx, "B200", &opt, sizeof opt) carries (source/api/c_api.c:207-211 memcpy's it; the first field
+ * must be the device name because sched_prerun dereferences *(char**)options, scheduler.c:49).  Zero = default. */
+typedef struct tb200_device_option
+{
+    char* dev_name;
+    int32_t num_gpus;   /* 0: TG_B200_GPUS or 1 */
+    int32_t first_gpu;  /* CUDA ordinal of the first GPU of the group (TG_B200_GPU) */
+} tb200_device_option;
+
+/* Page-locked host memory for callers that want it.  tb200_graph_run does not require it: a pageable caller buffer is
+ * page-locked in place (cudaHostRegister) the first time it is seen and stays registered until postrun. */
 TB200_API void* tb200_host_alloc(size_t bytes);
 TB200_API void tb200_host_free(void* p);
 
@@ -154,6 +182,7 @@ TB200_API void tb200_host_free(void* p);
 #define TB200_PRERUN_NO_WEIGHTS 1 /* allocate the packed-weight arena but leave it for a broadcast to fill */
 #define TB200_PRERUN_NO_GRAPH 2   /* do not capture a CUDA graph (debug / profiling by kernel)          */
 #define TB200_PRERUN_NO_TENSORCORE 4 /* route every conv through the CUDA-core direct kernels (cross-check) */
+#define TB200_PRERUN_POISON_ARENA 8  /* fill the activation arena with 0xA5 instead of 0 (tests: producers own their pad lanes) */
 
 /* interface->pre_run (device.h:47; cuda precedent cuda_graph.cc:36-42, cuda_executor.cc:136-180):
  * validate, choose a kernel per layer, pre-pack weights/bias/scales into ONE device arena (the analogue of
@@ -181,6 +210,14 @@ TB200_API int tb200_graph_postrun(tb200_graph* g);
 /* Packed-weight arena (device pointer + size): the object of the single NCCL broadcast at prerun when the
  * batch is sharded over several GPUs; identical layout on every rank for identical graphs. */
 TB200_API int tb200_graph_weight_arena(tb200_graph* g, void** device_ptr, size_t* bytes);
+
+/* multi-GPU contexts: re-send the arena (after a caller filled GPU 0's arena itself, TB200_PRERUN_NO_WEIGHTS) */
+TB200_API int tb200_graph_broadcast_weights(tb200_graph* g);
+/* how the batch was cut: shard `index` runs images [first_image, first_image + num_images) on CUDA device *cuda_device */
+TB200_API int tb200_graph_num_shards(tb200_graph* g);
+TB200_API int tb200_graph_shard(tb200_graph* g, int index, int* cuda_device, int* first_image, int* num_images);
+/* bytes of the activation arena of GPU 0's shard, what it would be without slot reuse, and of the weight arena */
+TB200_API int tb200_graph_arena_bytes(tb200_graph* g, size_t* activation_bytes, size_t* unshared_bytes, size_t* weight_bytes);
 
 /* Introspection for tests / bench / TG_DEBUG_TIME-style reports */
 TB200_API int tb200_graph_num_launches(tb200_graph* g);            /* kernels launched per tb200_graph_launch */

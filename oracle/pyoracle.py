@@ -76,7 +76,7 @@ class Reference:
         outs = [np.zeros(g.dims(t), dtype=g.np_dtype) for t in want]
         inp = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
         outp = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
-        stats = (C.c_double * 2)()
+        stats = (C.c_double * 4)()
         saved = {}
         for k, v in (env or {}).items():
             saved[k] = os.environ.get(k)
@@ -94,7 +94,46 @@ class Reference:
                     os.environ[k] = v
         if rc != 0:
             raise RuntimeError(f"reference run failed rc={rc}")
+        self.last_stats = tuple(stats)  # (min ms, avg ms, completed runs, elapsed ms)
         return dict(zip(want, outs)), (stats[0], stats[1])
+
+
+def run_tmfile(ref, path, x, out_shapes, device=None, precision=3, threads=8, warmup=0, loops=1, num_gpus=0, env=None):
+    """Run a tmfile through the library's serializer + run_graph on `device` (tm_benchmark's call sequence).  x: NCHW batch;
+    out_shapes: shapes of the graph outputs for this batch.  precision: TENGINE_MODE_UINT8 = 3, INT8 = 4.
+    num_gpus > 0: pass a tb200_device_option blob through set_context_device.  Returns (outputs, (min_ms, avg_ms))."""
+    x = np.ascontiguousarray(x)
+    outs = [np.zeros(s, dtype=x.dtype) for s in out_shapes]
+    nbytes = (C.c_int64 * len(outs))(*[o.nbytes for o in outs])
+    outp = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+    dims = (C.c_int * 4)(*x.shape)
+    stats = (C.c_double * 2)()
+
+    class Opt(C.Structure):
+        _fields_ = [("dev_name", C.c_char_p), ("num_gpus", C.c_int32), ("first_gpu", C.c_int32)]
+
+    blob, blob_size = None, 0
+    if num_gpus and device:
+        blob = Opt(device.encode(), int(num_gpus), 0)
+        blob_size = C.sizeof(Opt)
+    saved = {}
+    for k, v in (env or {}).items():
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        ref.lib.ref_shim_run_tmfile.restype = C.c_int
+        rc = ref.lib.ref_shim_run_tmfile(path.encode(), device.encode() if device else None, C.byref(blob) if blob else None, blob_size,
+                                         int(precision), dims, C.c_void_p(x.ctypes.data), len(outs), outp, nbytes, int(threads), int(warmup),
+                                         int(loops), stats)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if rc != 0:
+        raise RuntimeError(f"run_tmfile failed rc={rc}")
+    return outs, (stats[0], stats[1])
 
 
 def save_tmfile(ref, g, path):

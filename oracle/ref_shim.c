@@ -30,7 +30,10 @@
 #include "operator/prototype/eltwise_param.h"
 #include "operator/prototype/concat_param.h"
 #include "operator/prototype/upsample_param.h"
+#include "operator/prototype/softmax_param.h"
+#include "operator/prototype/flatten_param.h"
 #include "operator/op.h"
+#include <unistd.h>
 
 #include "../include/tengine_b200.h"
 
@@ -142,6 +145,10 @@ static int build_graph(struct built* B, const tb200_tensor_desc* tensors, int nu
         case TB200_OP_CONCAT: opname = "Concat"; break;
         case TB200_OP_UPSAMPLE: opname = "Upsample"; break;
         case TB200_OP_IDENTITY: opname = "Dropout"; break;
+        case TB200_OP_SOFTMAX: opname = "Softmax"; break;
+        case TB200_OP_SIGMOID: opname = "Sigmoid"; break;
+        case TB200_OP_HARDSWISH: opname = "Hardswish"; break;
+        case TB200_OP_RESHAPE: opname = "Flatten"; break; /* [N,C,H,W] -> [N,C*H*W,1,1]: the only reshape the five graphs contain */
         default: goto fail;
         }
         /* Const nodes are created BEFORE the node that consumes them: the tmfile writer and the graph splitter assume
@@ -172,7 +179,7 @@ static int build_graph(struct built* B, const tb200_tensor_desc* tensors, int nu
             {
                 int wz = L->weight_zero;
                 wt = make_const(graph, name, TENGINE_DT_UINT8, wdims, wn, L->weight, wbytes, L->weight_scales, &wz, 1);
-                bscales[0] = din->scale * L->weight_scales[0];
+                bscales[0] = (L->op == TB200_OP_FC && L->bias_scale != 0.f) ? L->bias_scale : din->scale * L->weight_scales[0];
             }
             else
             {
@@ -248,6 +255,8 @@ static int build_graph(struct built* B, const tb200_tensor_desc* tensors, int nu
         }
         case TB200_OP_CONCAT: ((struct concat_param*)pm)->axis = L->axis; break;
         case TB200_OP_UPSAMPLE: ((struct upsample_param*)pm)->scale = (float)L->up_scale; break;
+        case TB200_OP_SOFTMAX: ((struct softmax_param*)pm)->axis = L->axis; break;
+        case TB200_OP_RESHAPE: ((struct flatten_param*)pm)->axis = 1, ((struct flatten_param*)pm)->end_axis = 3; break;
         default: break;
         }
     }
@@ -353,16 +362,30 @@ SHIM_API int ref_shim_run(const tb200_tensor_desc* tensors, int num_tensors, con
     for (int i = 0; i < warmup; i++)
         if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
     {
+        /* Fleet mode (bench.py's CPU arm): REF_SHIM_WINDOW="<start epoch ms> <end epoch ms>" -- every worker process waits for
+         * the common start, then counts the run_graph() calls it COMPLETES before the common end.  Fleet throughput =
+         * sum of counts / window, which a starved or late worker lowers by its own share only. */
+        double w0 = 0, w1 = 0;
+        const char* win = getenv("REF_SHIM_WINDOW");
+        const int fleet = win && sscanf(win, "%lf %lf", &w0, &w1) == 2 && w1 > w0;
         double mn = 1e30, sum = 0;
-        for (int i = 0; i < loops; i++)
+        int done = 0;
+        if (fleet)
+            while (now_ms() < w0) usleep(200);
+        const double t_begin = now_ms();
+        for (int i = 0; fleet ? 1 : (i < loops); i++)
         {
             double t0 = now_ms();
+            if (fleet && t0 >= w1) break;
             if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
-            double dt = now_ms() - t0;
+            double t1 = now_ms();
+            if (fleet && t1 > w1) break; /* finished after the window closed: not counted */
+            double dt = t1 - t0;
             if (dt < mn) mn = dt;
             sum += dt;
+            done++;
         }
-        if (ms_stats) ms_stats[0] = mn, ms_stats[1] = loops ? sum / loops : 0;
+        if (ms_stats) ms_stats[0] = mn, ms_stats[1] = done ? sum / done : 0, ms_stats[2] = done, ms_stats[3] = now_ms() - t_begin;
     }
     for (int i = 0; i < num_want; i++)
     {
@@ -392,12 +415,101 @@ SHIM_API int ref_shim_save_tmfile(const tb200_tensor_desc* tensors, int num_tens
     int rc = build_graph(&B, tensors, num_tensors, layers, num_layers, input_ids, num_inputs, output_ids, num_outputs, NULL, NULL);
     if (rc != 0) return rc;
     if (infer_ir_graph_shape((struct graph*)B.graph) != 0) rc = -110;
-    else rc = ref_shim_save_graph_cxx(B.graph, fname);
+    else
+    {
+        /* The tmfile's pad fields are what the loader turns into pad_*_org (serializer/tmfile/op/tm2_pool.c:56-64), from which
+         * infer_shape derives the real pads again (operator/prototype/pooling.c:68-92): store the *_org values, as a
+         * converter-written model does. */
+        struct graph* g = (struct graph*)B.graph;
+        for (int i = 0; i < g->node_num; i++)
+            if (g->node_list[i]->op.type == OP_POOL)
+            {
+                struct pool_param* p = (struct pool_param*)g->node_list[i]->op.param_mem;
+                p->pad_h0 = p->pad_h0_org, p->pad_h1 = p->pad_h1_org, p->pad_w0 = p->pad_w0_org, p->pad_w1 = p->pad_w1_org;
+            }
+        rc = ref_shim_save_graph_cxx(B.graph, fname);
+    }
     free_built(&B, num_tensors);
     return rc;
 }
 
 SHIM_API const char* ref_shim_version(void) { return get_tengine_version(); }
+
+/* Load a tmfile with the reference's serializer and run it on a named device ("CPU" / NULL, or e.g. "B200") exactly the way
+ * tm_benchmark does (create_context + set_context_device + create_graph + set_tensor_shape/buffer + prerun_graph_multithread +
+ * run_graph, benchmark/tm_benchmark.cc:60-135), with a caller-supplied NCHW input of `batch` images; copies graph output i
+ * into out_bufs[i] (out_bytes[i] bytes available; the real size is written back).  precision: TENGINE_MODE_*.  opt_blob: the
+ * device's option struct for set_context_device (may be NULL). */
+SHIM_API int ref_shim_run_tmfile(const char* fname, const char* device_name, const void* opt_blob, int opt_size, int precision, const int* in_dims,
+                                 const void* in_buf, int num_out, void* const* out_bufs, int64_t* out_bytes, int num_thread, int warmup, int loops,
+                                 double* ms_stats)
+{
+    if (!g_inited)
+    {
+        if (init_tengine() != 0) return -100;
+        g_inited = 1;
+    }
+    int rc = -1;
+    context_t ctx = NULL;
+    if (device_name && strcmp(device_name, "CPU") != 0)
+    {
+        ctx = create_context("shim_ctx", 1);
+        if (set_context_device(ctx, device_name, opt_blob, opt_size) < 0)
+        {
+            fprintf(stderr, "ref_shim: device %s not available\n", device_name);
+            destroy_context(ctx);
+            return -101;
+        }
+    }
+    graph_t graph = create_graph(ctx, "tengine", fname);
+    if (!graph)
+    {
+        if (ctx) destroy_context(ctx);
+        return -102;
+    }
+    tensor_t it = get_graph_input_tensor(graph, 0, 0);
+    int64_t in_bytes = (int64_t)in_dims[0] * in_dims[1] * in_dims[2] * in_dims[3];
+    if (!it || set_tensor_shape(it, in_dims, 4) < 0 || set_tensor_buffer(it, (void*)in_buf, (int)in_bytes) < 0) goto done;
+    struct options opt;
+    opt.num_thread = num_thread, opt.cluster = TENGINE_CLUSTER_ALL, opt.precision = precision, opt.affinity = 0;
+    if (prerun_graph_multithread(graph, opt) < 0)
+    {
+        rc = -103;
+        goto done;
+    }
+    repin_from_env(num_thread);
+    for (int i = 0; i < warmup; i++)
+        if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
+    {
+        double mn = 1e30, sum = 0;
+        for (int i = 0; i < loops; i++)
+        {
+            double t0 = now_ms();
+            if (run_graph(graph, 1) < 0) { rc = -105; goto done_postrun; }
+            double dt = now_ms() - t0;
+            if (dt < mn) mn = dt;
+            sum += dt;
+        }
+        if (ms_stats) ms_stats[0] = mn, ms_stats[1] = loops ? sum / loops : 0;
+    }
+    if (get_graph_output_node_number(graph) < num_out) { rc = -107; goto done_postrun; }
+    for (int i = 0; i < num_out; i++)
+    {
+        tensor_t ot = get_graph_output_tensor(graph, i, 0);
+        const int64_t bytes = ot ? get_tensor_buffer_size(ot) : 0;
+        void* p = ot ? get_tensor_buffer(ot) : NULL;
+        if (!p || bytes > out_bytes[i]) { rc = -106; goto done_postrun; }
+        memcpy(out_bufs[i], p, (size_t)bytes);
+        out_bytes[i] = bytes;
+    }
+    rc = 0;
+done_postrun:
+    postrun_graph(graph);
+done:
+    destroy_graph(graph);
+    if (ctx) destroy_context(ctx);
+    return rc;
+}
 
 /* Print op + parameters of every non-const node of a tmfile (used to mirror the reference's benchmark graphs in
  * tengine_b200/workloads.py). */

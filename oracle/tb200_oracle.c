@@ -525,6 +525,106 @@ ORACLE_API int tb200_oracle_upsample(const tb200_tensor_desc* tin, const void* x
     return 0;
 }
 
+/* ---- sigmoid: sigmoid/sigmoid_ref.c:84-127 (int8), :129-172 (uint8).  The reference's MIN(x, 30) result is overwritten by
+ *      its MAX(x, -30) line (:110-111), so only the lower clamp acts; exp() runs in double on the float argument. ------------ */
+ORACLE_API int tb200_oracle_sigmoid(const tb200_tensor_desc* tin, const void* x, const tb200_tensor_desc* tout, void* y)
+{
+    const size_t total = (size_t)tin->dims[0] * tin->dims[1] * tin->dims[2] * tin->dims[3];
+    const int u8 = tin->data_type == TB200_DT_UINT8;
+    for (size_t i = 0; i < total; i++)
+    {
+        const float q = u8 ? (float)((const uint8_t*)x)[i] : (float)((const int8_t*)x)[i];
+        float in = (q - (float)tin->zero_point) * tin->scale;
+        float o = (in > -30.0f) ? in : -30.0f;
+        o = 1 / (1 + exp(-o));
+        int v = round(o / tout->scale + tout->zero_point);
+        if (u8)
+        {
+            if (v > 255) v = 255;
+            else if (v < 0) v = 0;
+            ((uint8_t*)y)[i] = (uint8_t)v;
+        }
+        else
+        {
+            if (v > 127) v = 127;
+            else if (v < -127) v = -127;
+            ((int8_t*)y)[i] = (int8_t)v;
+        }
+    }
+    return 0;
+}
+
+/* ---- hardswish, uint8 only as in the reference: hardswish/hardswish_kernel_ref_uint8.c:41-80 --------------------------- */
+ORACLE_API int tb200_oracle_hardswish_uint8(const tb200_tensor_desc* tin, const uint8_t* x, const tb200_tensor_desc* tout, uint8_t* y)
+{
+    const size_t total = (size_t)tin->dims[0] * tin->dims[1] * tin->dims[2] * tin->dims[3];
+    for (size_t i = 0; i < total; i++)
+    {
+        float d = ((float)x[i] - (float)tin->zero_point) * tin->scale;
+        float tmp = d + 3.f;
+        if (tmp < 0.f) tmp = 0.f;
+        if (tmp > 6.f) tmp = 6.f;
+        d = d * (tmp / 6.f);
+        int v = round(d / tout->scale + tout->zero_point);
+        if (v > 255) v = 255;
+        else if (v < 0) v = 0;
+        y[i] = (uint8_t)v;
+    }
+    return 0;
+}
+
+/* ---- softmax over axis 1 of an NCHW tensor: softmax/softmax_kernel_ref_int8.c:41-118, softmax_kernel_ref_uint8.c:41-120,
+ *      GetMaxArray / GetOutResult of softmax_kernel_ref.h:36-82 (float max, exp in double stored to float, float running sum in
+ *      channel order, float division) ------------------------------------------------------------------------------------------ */
+ORACLE_API int tb200_oracle_softmax(const tb200_tensor_desc* tin, const void* x, const tb200_tensor_desc* tout, void* y)
+{
+    const int N = tin->dims[0], C = tin->dims[1], HW = tin->dims[2] * tin->dims[3];
+    const int u8 = tin->data_type == TB200_DT_UINT8;
+    float* f = (float*)malloc(sizeof(float) * (size_t)C * HW);
+    float* o = (float*)malloc(sizeof(float) * (size_t)C * HW);
+    float* mx = (float*)malloc(sizeof(float) * HW);
+    float* sum = (float*)malloc(sizeof(float) * HW);
+    for (int n = 0; n < N; n++)
+    {
+        const size_t base = (size_t)n * C * HW;
+        for (size_t i = 0; i < (size_t)C * HW; i++)
+            f[i] = u8 ? ((float)((const uint8_t*)x)[base + i] - (float)(uint8_t)tin->zero_point) * tin->scale
+                      : (float)((const int8_t*)x)[base + i] * tin->scale;
+        memcpy(mx, f, sizeof(float) * HW);
+        for (int j = 0; j < C; j++)
+            for (int l = 0; l < HW; l++)
+                if (mx[l] < f[j * HW + l]) mx[l] = f[j * HW + l];
+        memset(sum, 0, sizeof(float) * HW);
+        for (int j = 0; j < C; j++)
+            for (int l = 0; l < HW; l++)
+            {
+                o[j * HW + l] = exp(f[j * HW + l] - mx[l]);
+                sum[l] += o[j * HW + l];
+            }
+        for (int j = 0; j < C; j++)
+            for (int l = 0; l < HW; l++) o[j * HW + l] /= sum[l];
+        for (size_t i = 0; i < (size_t)C * HW; i++)
+        {
+            if (u8)
+            {
+                int v = (int)(round(o[i] / tout->scale) + (uint8_t)tout->zero_point);
+                if (v > 255) v = 255;
+                else if (v < 0) v = 0;
+                ((uint8_t*)y)[base + i] = (uint8_t)v;
+            }
+            else
+            {
+                int v = round(o[i] / tout->scale);
+                if (v > 127) v = 127;
+                else if (v < -127) v = -127;
+                ((int8_t*)y)[base + i] = (int8_t)v;
+            }
+        }
+    }
+    free(f), free(o), free(mx), free(sum);
+    return 0;
+}
+
 /* ---- run a whole layer list on host NCHW buffers (buffers[i] is tensor i; inputs filled by the caller) */
 ORACLE_API int tb200_oracle_run(const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers,
                                 int num_layers, void* const* buffers, int uint8_mode)
@@ -567,9 +667,13 @@ ORACLE_API int tb200_oracle_run(const tb200_tensor_desc* tensors, int num_tensor
         }
         case TB200_OP_UPSAMPLE: rc = tb200_oracle_upsample(tin, x, tout, y, L); break;
         case TB200_OP_IDENTITY:
+        case TB200_OP_RESHAPE: /* flatten/flatten_ref.c:49-83, reshape: the same bytes in NCHW order */
             memcpy(y, x, (size_t)tin->dims[0] * tin->dims[1] * tin->dims[2] * tin->dims[3]);
             rc = 0;
             break;
+        case TB200_OP_SIGMOID: rc = tb200_oracle_sigmoid(tin, x, tout, y); break;
+        case TB200_OP_HARDSWISH: rc = u8 ? tb200_oracle_hardswish_uint8(tin, x, tout, y) : -1; break;
+        case TB200_OP_SOFTMAX: rc = (L->axis == 1) ? tb200_oracle_softmax(tin, x, tout, y) : -1; break;
         default: rc = -1;
         }
         if (rc != 0) return -(i + 1);

@@ -5,19 +5,20 @@ tengine_b200/device/ -- but tests and bench.py drive the same C ABI through thes
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # TENGINE_DT_* (source/api/c_api.h:58-63)
 DT_FP32, DT_INT8, DT_UINT8, DT_INT32 = 0, 2, 3, 4
 
-OP_CONV, OP_FC, OP_POOL, OP_RELU, OP_ELTWISE, OP_CONCAT, OP_UPSAMPLE, OP_IDENTITY = range(8)
-OP_NAMES = ["conv", "fc", "pool", "relu", "eltwise", "concat", "upsample", "identity"]
+(OP_CONV, OP_FC, OP_POOL, OP_RELU, OP_ELTWISE, OP_CONCAT, OP_UPSAMPLE, OP_IDENTITY, OP_SOFTMAX, OP_SIGMOID, OP_HARDSWISH,
+ OP_RESHAPE) = range(12)
+OP_NAMES = ["conv", "fc", "pool", "relu", "eltwise", "concat", "upsample", "identity", "softmax", "sigmoid", "hardswish", "reshape"]
 
 RECIPE_HCL, RECIPE_REF = 0, 1
 ELT_PROD, ELT_SUM = 0, 2
 POOL_MAX, POOL_AVG = 0, 1
 
-PRERUN_DEFAULT, PRERUN_NO_WEIGHTS, PRERUN_NO_GRAPH, PRERUN_NO_TENSORCORE = 0, 1, 2, 4
+PRERUN_DEFAULT, PRERUN_NO_WEIGHTS, PRERUN_NO_GRAPH, PRERUN_NO_TENSORCORE, PRERUN_POISON_ARENA = 0, 1, 2, 4, 8
 
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -55,7 +56,9 @@ class KConvShape(C.Structure):
 # every symbol include/tengine_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "tb200_abi_version", "tb200_last_error", "tb200_device_count", "tb200_context_create", "tb200_context_destroy",
-    "tb200_context_stream", "tb200_host_alloc", "tb200_host_free", "tb200_graph_prerun", "tb200_graph_run",
+    "tb200_context_stream", "tb200_context_create_multi", "tb200_context_num_gpus", "tb200_context_gpu", "tb200_context_stream_of",
+    "tb200_context_broadcast_kind", "tb200_graph_broadcast_weights", "tb200_graph_num_shards", "tb200_graph_shard", "tb200_graph_arena_bytes",
+    "tb200_host_alloc", "tb200_host_free", "tb200_graph_prerun", "tb200_graph_run",
     "tb200_graph_upload", "tb200_graph_launch", "tb200_graph_download", "tb200_graph_sync", "tb200_graph_postrun",
     "tb200_graph_weight_arena", "tb200_graph_num_launches", "tb200_graph_layer_kernel", "tb200_graph_read_tensor",
     "tb200_graph_profile", "tb200_graph_work", "tb200k_cpad", "tb200k_conv_direct", "tb200k_conv_dw3x3",

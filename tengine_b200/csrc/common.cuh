@@ -24,6 +24,7 @@ struct EpiParams
     const float* w_scale; // [OCp]
     float in_scale, out_scale;
     float in_w_scale;     // uint8: s_in * s_w (per tensor), computed once on the host in fp32
+    float bias_scale;     // uint8 FC: the bias tensor's own scale (fc_ref.c:141-146); == in_w_scale for convolutions
     int32_t in_zero, w_zero, out_zero;
     int32_t activation;
     int32_t recipe;
@@ -107,8 +108,8 @@ static __device__ __noinline__ int requant(int32_t acc, int oc, const EpiParams&
         int q;
         if (e.fc_rounding)
         {
-            // fc_ref.c:146,162: data = bias*bias_scale + sum ; roundf(data / s_out) + zp  (bias_scale == s_in*s_w)
-            if (e.has_bias) f = __fadd_rn(f, __fmul_rn((float)b, e.in_w_scale));
+            // fc_ref.c:146,162: data = bias*bias_scale + sum ; roundf(data / s_out) + zp  (bias_scale: the bias tensor's scale)
+            if (e.has_bias) f = __fadd_rn(f, __fmul_rn((float)b, e.bias_scale));
             q = (int)roundf(__fdiv_rn(f, e.out_scale)) + e.out_zero;
         }
         else

@@ -5,7 +5,10 @@
 // cpu_device.c:62-95) and of conv_hcl_prerun's weight packing (conv_kernel_x86.c:2137-2209); run = the
 // analogue of cpu_device.c:97-221 with every node executing on the GPU.  No CPU compute path exists here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -19,6 +22,8 @@
 #include "kernels.h"
 
 using namespace tb200;
+
+#define TB200_OP_NOP_ (-1) // planner-internal: a node folded into its producer
 
 // ---- error reporting -------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -37,12 +42,61 @@ static int fail(int code, const char* fmt, ...)
         if (_e != cudaSuccess) return fail(TB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+// A registered (page-locked) range of caller memory: tb200_graph_run pins the application's NCHW buffers the first time it
+// sees them (cudaHostRegister, portable across the group's GPUs) so that every later H2D / D2H copy is a true async DMA.
+struct HostReg
+{
+    const uint8_t* p;
+    size_t bytes;
+    bool ours; // false: the range was already page-locked by the application (cudaHostAlloc / its own registration)
+};
+
+// One context per GPU.  A multi-GPU context (tb200_context_create_multi) is the context of GPU 0 plus `peers`
+// (GPUs 1..R-1), all driven by the calling thread; `comms` are the ncclComm_t of ncclCommInitAll over the group.
 struct tb200_context
 {
     int device;
     int num_sms;
     cudaStream_t stream;
+    std::vector<tb200_context*> peers;
+    std::vector<void*> comms; // [R] when NCCL is in use
+    const char* bcast_kind = "none";
+    std::vector<HostReg> host_regs;
+    std::vector<const void*> host_reg_failed;
 };
+
+// ---- NCCL, loaded at run time (libnccl.so.2: the copy torch already mapped when running under Python, the system one
+//      otherwise) so that single-GPU users never need it.  Only what the one broadcast at prerun needs. ----
+struct NcclApi
+{
+    void* handle = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    if (getenv("TB200_NO_NCCL")) return nullptr;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"})
+        if ((api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!api.handle) return nullptr;
+    api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.handle, "ncclCommInitAll");
+    api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+    api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast && api.GetErrorString;
+    return api.ok ? &api : nullptr;
+}
 
 enum StepKind
 {
@@ -59,10 +113,15 @@ enum StepKind
     K_POINTWISE,
     K_CONCAT_PART,
     K_UPSAMPLE,
-    K_COPY
+    K_COPY,
+    K_LUT,
+    K_SOFTMAX,
+    K_RESHAPE,
+    K_NONE // a node folded into its producer
 };
 static const char* kStepName[] = {"nchw_to_nhwc", "nhwc_to_nchw", "conv_stem_nchw_dp4a", "conv_stem_nchw_tcgen05", "conv_gather_tcgen05", "conv_dw_direct", "conv_direct_dp4a",
-                                  "gemm_i8_tcgen05", "conv_igemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy"};
+                                  "gemm_i8_tcgen05", "conv_igemm_i8_tcgen05", "pool", "pointwise", "concat_requant", "upsample_nearest", "copy",
+                                  "byte_lut", "softmax", "reshape_nchw_order", "fused_into_producer"};
 
 struct Step
 {
@@ -79,10 +138,14 @@ struct Step
     GemmPlan gemm{};
     const int32_t* btab = nullptr; // uint8 tensor-core kinds: padding-tap corrections
     DwPlan dwp{};
+    WindowPlan wp{}; // K_GATHER_TC: TMA-staged input window (conv_window.cu) when applicable
     long long bytes = 0; // pointwise / copy
     // concat / layout
     long long npix = 0;
     int c = 0, cp_in = 0, cp_out = 0, c_off = 0, n = 0, h = 0, w_ = 0, scale = 0;
+    int c_write = 0;             // concat: channels written from c_off (the last input also clears the pad lanes)
+    int oc_ = 0, oh_ = 0, ow_ = 0; // reshape: output dims
+    void* scratch = nullptr;     // reshape: NCHW-ordered staging
     int nhwc16 = 0; // K_GATHER_TC: the input is a 16-channel NHWC tensor (else the NCHW network input)
     float s_in = 0, s_out = 0;
     int z_in = 0, z_out = 0;
@@ -95,6 +158,8 @@ struct TensorInfo
     int cp;
     size_t nhwc_bytes, nchw_bytes;
     size_t off; // offset in the activation arena
+    size_t slot_bytes = 0;
+    int first_def = INT_MAX, last_use = -1; // liveness in layer order (arena slot reuse)
     uint8_t* dev = nullptr;
     int input_index = -1, output_index = -1;
     bool nhwc_needed = false; // graph inputs: a consumer needs the NHWC copy
@@ -122,8 +187,12 @@ struct tb200_graph
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_out;
     cudaEvent_t ev_done = nullptr;
-    double work_ops = 0, work_bytes = 0;
+    double work_ops = 0, work_bytes = 0, work_wbytes = 0;
     int num_launches = 0;
+    // batch sharding over the GPUs of a multi-GPU context: this graph is the shard of GPU 0 and owns the others
+    std::vector<tb200_graph*> shards;
+    int first_image = 0, num_images = 0, total_images = 0;
+    size_t act_unshared_bytes = 0; // what the arena would need without slot reuse (introspection)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -151,9 +220,8 @@ int tb200_device_count(void)
     return good;
 }
 
-int tb200_context_create(int cuda_device, tb200_context** out)
+static int context_create_one(int cuda_device, tb200_context** out)
 {
-    if (!out) return fail(TB200_ERR_INVALID, "null out");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
     {
@@ -167,17 +235,82 @@ int tb200_context_create(int cuda_device, tb200_context** out)
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device));
     if (major != 10) return fail(TB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this backend is built for sm_100a only", cuda_device, major, minor);
     CUDA_OK(cudaSetDevice(cuda_device));
+    cudaStream_t st;
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     tb200_context* c = new tb200_context();
     c->device = cuda_device;
     c->num_sms = sms;
-    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->stream = st;
     *out = c;
+    return 0;
+}
+
+static void host_unregister_all(tb200_context* ctx)
+{
+    for (const HostReg& r : ctx->host_regs)
+        if (r.ours && cudaHostUnregister((void*)r.p) != cudaSuccess) cudaGetLastError(); // the owner may have freed it already
+    ctx->host_regs.clear();
+    ctx->host_reg_failed.clear();
+}
+
+int tb200_context_create(int cuda_device, tb200_context** out)
+{
+    if (!out) return fail(TB200_ERR_INVALID, "null out");
+    return context_create_one(cuda_device, out);
+}
+
+// one process drives R GPUs; the batch of every run is cut into R contiguous slices of dim 0.  The packed
+// weight arena is built once (GPU 0) and reaches the other GPUs by ONE grouped ncclBroadcast at prerun (communicators from
+// ncclCommInitAll); there is no collective in the steady state.  A device listed twice (tests on a one-GPU box) rules NCCL
+// out (it refuses duplicate devices): the arena then travels by cudaMemcpyPeerAsync, everything else is identical.
+int tb200_context_create_multi(const int* cuda_devices, int num_devices, tb200_context** out)
+{
+    if (!out || !cuda_devices || num_devices < 1 || num_devices > 64) return fail(TB200_ERR_INVALID, "bad device list");
+    tb200_context* root = nullptr;
+    int rc = context_create_one(cuda_devices[0], &root);
+    if (rc) return rc;
+    bool distinct = true;
+    for (int i = 1; i < num_devices; i++)
+    {
+        tb200_context* p = nullptr;
+        if ((rc = context_create_one(cuda_devices[i], &p)) != 0)
+        {
+            tb200_context_destroy(root);
+            return rc;
+        }
+        root->peers.push_back(p);
+        for (int j = 0; j < i; j++) distinct &= cuda_devices[j] != cuda_devices[i];
+    }
+    if (num_devices > 1)
+    {
+        root->bcast_kind = "memcpy_peer";
+        NcclApi* nc = distinct ? nccl_api() : nullptr;
+        if (nc)
+        {
+            std::vector<void*> comms(num_devices, nullptr);
+            const int r = nc->CommInitAll(comms.data(), num_devices, cuda_devices);
+            if (r == 0)
+                root->comms = comms, root->bcast_kind = "nccl";
+            else
+                fprintf(stderr, "tengine_b200: ncclCommInitAll failed (%s); the weight arena will be broadcast with cudaMemcpyPeer\n", nc->GetErrorString(r));
+        }
+        else if (distinct && !getenv("TB200_NO_NCCL"))
+            fprintf(stderr, "tengine_b200: libnccl.so.2 not found; the weight arena will be broadcast with cudaMemcpyPeer\n");
+        cudaSetDevice(cuda_devices[0]);
+    }
+    *out = root;
     return 0;
 }
 
 int tb200_context_destroy(tb200_context* ctx)
 {
     if (!ctx) return 0;
+    host_unregister_all(ctx);
+    if (!ctx->comms.empty())
+        if (NcclApi* nc = nccl_api())
+            for (void* c : ctx->comms)
+                if (c) nc->CommDestroy(c);
+    for (tb200_context* p : ctx->peers) tb200_context_destroy(p);
     cudaSetDevice(ctx->device);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -185,6 +318,23 @@ int tb200_context_destroy(tb200_context* ctx)
 }
 
 void* tb200_context_stream(tb200_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int tb200_context_num_gpus(tb200_context* ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
+static tb200_context* context_of(tb200_context* ctx, int index)
+{
+    if (!ctx || index < 0 || index > (int)ctx->peers.size()) return nullptr;
+    return index == 0 ? ctx : ctx->peers[index - 1];
+}
+int tb200_context_gpu(tb200_context* ctx, int index)
+{
+    tb200_context* c = context_of(ctx, index);
+    return c ? c->device : -1;
+}
+void* tb200_context_stream_of(tb200_context* ctx, int index)
+{
+    tb200_context* c = context_of(ctx, index);
+    return c ? (void*)c->stream : nullptr;
+}
+const char* tb200_context_broadcast_kind(tb200_context* ctx) { return ctx ? ctx->bcast_kind : "none"; }
 
 void* tb200_host_alloc(size_t bytes)
 {
@@ -216,6 +366,7 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
     e.fc_rounding = fc ? 1 : 0;
     e.has_bias = L.bias != nullptr;
     e.in_w_scale = e.is_uint8 ? tin.scale * L.weight_scales[0] : 0.f; // fp32 product, as bias_scale in conv_kernel_x86.c:1723
+    e.bias_scale = (fc && e.is_uint8 && L.bias_scale != 0.f) ? L.bias_scale : e.in_w_scale; // fc_ref.c:141-146
     // fast-path constants (common.cuh requant_fast): clamps of t = f / s_out with activation and saturation folded in
     const float so = tout.scale;
     const float inf = __builtin_inff();
@@ -285,7 +436,9 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_NHWC2NCHW: err = launch_nhwc_to_nchw(s.in, s.out, s.n, s.c, s.h, s.w_, st); break;
     case K_CONV_STEM: err = launch_conv_stem(s.in, s.w, s.out, s.cs, s.epi, st); break;
     case K_STEM_TC: err = launch_stem_tc(s.dwp, s.in, s.w, s.out, s.cs, s.epi, st); break;
-    case K_GATHER_TC: err = launch_conv_gather_tc(s.in, s.w, s.out, s.cs, s.epi, s.nhwc16, st); break;
+    case K_GATHER_TC:
+        err = s.wp.valid ? launch_conv_window(s.wp, s.w, s.out, s.cs, s.epi, st) : launch_conv_gather_tc(s.in, s.w, s.out, s.cs, s.epi, s.nhwc16, st);
+        break;
     case K_CONV_DW:
         err = s.dwp.valid ? launch_conv_dw_tma(s.dwp, s.w, s.out, s.cs, s.epi, st) : launch_conv_dw(s.in, s.w, s.out, s.cs, s.epi, st);
         break;
@@ -295,7 +448,13 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
     case K_POINTWISE: err = launch_pointwise(s.in, s.in2, s.out, s.bytes, s.pp, s.u8, st); break;
     case K_CONCAT_PART:
-        err = launch_concat_part(s.in, s.out, s.npix, s.c, s.cp_in, s.cp_out, s.c_off, s.s_in, s.z_in, s.s_out, s.z_out, s.u8, st);
+        err = launch_concat_part(s.in, s.out, s.npix, s.c, s.c_write, s.cp_in, s.cp_out, s.c_off, s.s_in, s.z_in, s.s_out, s.z_out, s.u8, st);
+        break;
+    case K_LUT: err = launch_byte_lut(s.in, s.out, (const uint8_t*)s.w, s.bytes, s.c, s.cp_in, st); break;
+    case K_SOFTMAX: err = launch_softmax(s.in, s.out, s.npix, s.c, s.cp_in, s.s_in, s.z_in, s.s_out, s.z_out, s.u8, st); break;
+    case K_RESHAPE:
+        err = launch_nhwc_to_nchw(s.in, s.scratch, s.n, s.c, s.h, s.w_, st);
+        if (err == cudaSuccess) err = launch_nchw_to_nhwc(s.scratch, s.out, s.n, s.oc_, s.oh_, s.ow_, st);
         break;
     case K_UPSAMPLE: err = launch_upsample(s.in, s.out, s.n, s.h, s.w_, s.cp_in, s.scale, st); break;
     case K_COPY: err = cudaMemcpyAsync(s.out, s.in, (size_t)s.bytes, cudaMemcpyDeviceToDevice, st); break;
@@ -307,6 +466,8 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
 static void destroy_graph(tb200_graph* g)
 {
     if (!g) return;
+    for (tb200_graph* sh : g->shards) destroy_graph(sh);
+    g->shards.clear();
     cudaSetDevice(g->ctx->device);
     for (auto e : g->cu_execs) if (e) cudaGraphExecDestroy(e);
     for (auto c : g->cu_graphs) if (c) cudaGraphDestroy(c);
@@ -322,15 +483,78 @@ static void destroy_graph(tb200_graph* g)
     delete g;
 }
 
-extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* tensors, int num_tensors,
-                                  const tb200_layer_desc* layers, int num_layers, const int32_t* input_ids, int num_inputs,
-                                  const int32_t* output_ids, int num_outputs, int flags, tb200_graph** out)
+// Host-side tables of the unary byte ops (sigmoid, hardswish): inputs are bytes, so the op IS a 256-entry table, computed here
+// once per layer with the reference's own C arithmetic (libm exp in double, C round()) -- the device then only permutes bytes,
+// bit-exact by construction.  sigmoid/sigmoid_ref.c:84-127 (int8), :129-172 (uint8); hardswish/hardswish_kernel_ref_uint8.c:41-80.
+static void build_byte_lut(int op, bool u8, const tb200_tensor_desc& tin, const tb200_tensor_desc& tout, uint8_t* lut)
 {
-    if (!ctx || !tensors || !layers || !out || num_tensors <= 0 || num_layers <= 0) return fail(TB200_ERR_INVALID, "bad arguments");
+    for (int b = 0; b < 256; b++)
+    {
+        const float q = u8 ? (float)b : (float)(int)(int8_t)b;
+        volatile float x = (q - (float)tin.zero_point) * tin.scale;
+        volatile float y;
+        if (op == TB200_OP_SIGMOID)
+        {
+            float t = (x > -30.0f) ? x : -30.0f; // the reference's MIN(x, 30) is overwritten by its MAX(x, -30) (sigmoid_ref.c:110-111)
+            y = (float)(1 / (1 + exp((double)-t)));
+        }
+        else
+        {
+            volatile float tmp = x + 3.f;
+            if (tmp < 0.f) tmp = 0.f;
+            if (tmp > 6.f) tmp = 6.f;
+            volatile float r = tmp / 6.f;
+            y = x * r;
+        }
+        volatile float z = y / tout.scale;
+        volatile float zz = z + (float)tout.zero_point;
+        int v = (int)round((double)zz);
+        if (u8) v = v > 255 ? 255 : (v < 0 ? 0 : v);
+        else v = v > 127 ? 127 : (v < -127 ? -127 : v);
+        lut[b] = (uint8_t)(v & 0xff);
+    }
+}
+
+static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers, int num_layers,
+                      const int32_t* input_ids, int num_inputs, const int32_t* output_ids, int num_outputs, int flags, tb200_graph* g)
+{
     CUDA_OK(cudaSetDevice(ctx->device));
-    tb200_graph* g = new tb200_graph();
-    g->ctx = ctx, g->flags = flags;
-    auto bail = [&](int rc) { destroy_graph(g); return rc; };
+    auto bail = [&](int rc) { return rc; }; // the caller owns g and destroys it on failure (arenas, tensor maps, CUDA graphs, an open capture)
+
+    // ---- node fusion, decided from the descriptors alone.  Eltwise -> ReLU where the ReLU's output has its
+    //      input's quantisation (what the reference's quantisation tool writes, quant_save_graph.cpp:136-200) and the eltwise
+    //      result has no other reader: the ReLU is then max(byte, zero point) on the requantised bytes (relu_same_scale_kernel),
+    //      applied inside the eltwise kernel -- one pass over memory instead of two, the intermediate tensor is never stored.
+    //      Not under TB200_PRERUN_NO_GRAPH, whose contract is that every intermediate stays readable. ----
+    std::vector<tb200_layer_desc> fused(layers, layers + num_layers);
+    std::vector<int> post_relu(num_layers, 0);
+    if (!(flags & TB200_PRERUN_NO_GRAPH) && !getenv("TB200_NO_FUSION"))
+    {
+        std::vector<int> readers(num_tensors, 0), reader_layer(num_tensors, -1);
+        for (int li = 0; li < num_layers; li++)
+            for (int k = 0; k < layers[li].num_inputs && k < 4; k++)
+                if (layers[li].inputs[k] >= 0 && layers[li].inputs[k] < num_tensors) readers[layers[li].inputs[k]]++, reader_layer[layers[li].inputs[k]] = li;
+        std::vector<char> is_out(num_tensors, 0);
+        for (int i = 0; i < num_outputs; i++)
+            if (output_ids[i] >= 0 && output_ids[i] < num_tensors) is_out[output_ids[i]] = 1;
+        for (int li = 0; li < num_layers; li++)
+        {
+            const tb200_layer_desc& E = layers[li];
+            if (E.op != TB200_OP_ELTWISE || E.output < 0 || E.output >= num_tensors || readers[E.output] != 1 || is_out[E.output]) continue;
+            const int lj = reader_layer[E.output];
+            const tb200_layer_desc& R = layers[lj];
+            if (lj <= li || R.op != TB200_OP_RELU || R.negative_slope != 0.f || R.output < 0 || R.output >= num_tensors) continue;
+            const tb200_tensor_desc &ti = tensors[E.output], &to = tensors[R.output];
+            if (ti.scale != to.scale || ti.zero_point != to.zero_point || ti.data_type != to.data_type) continue;
+            if (ti.data_type == TB200_DT_UINT8 && (ti.dims[1] % 16)) continue; // pad lanes of uint8 tensors must stay 0, not the zero point
+            bool same = true;
+            for (int k = 0; k < 4; k++) same &= ti.dims[k] == to.dims[k];
+            if (!same) continue;
+            fused[li].output = R.output, post_relu[li] = 1;
+            fused[lj].op = TB200_OP_NOP_, fused[lj].num_inputs = 0;
+        }
+    }
+    layers = fused.data();
 
     // ---- tensors ----
     g->tensors.resize(num_tensors);
@@ -346,8 +570,8 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         t.cp = cpad(t.d.dims[1]);
         t.nhwc_bytes = (size_t)t.d.dims[0] * t.d.dims[2] * t.d.dims[3] * t.cp;
         t.nchw_bytes = (size_t)t.d.dims[0] * t.d.dims[1] * t.d.dims[2] * t.d.dims[3];
-        t.off = act;
-        act += align_up(t.nhwc_bytes, 1024);
+        t.off = 0;
+        t.slot_bytes = align_up(t.nhwc_bytes, 1024);
     }
     for (int i = 0; i < num_inputs; i++)
     {
@@ -373,6 +597,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
     for (int li = 0; li < num_layers; li++)
     {
         const tb200_layer_desc& L = layers[li];
+        if (L.op == TB200_OP_NOP_)
+        {
+            kind[li] = K_NONE;
+            continue;
+        }
         if (L.num_inputs < 1 || L.num_inputs > 4) return bail(fail(TB200_ERR_INVALID, "layer %d: num_inputs %d", li, L.num_inputs));
         for (int k = 0; k < L.num_inputs; k++)
             if (L.inputs[k] < 0 || L.inputs[k] >= num_tensors) return bail(fail(TB200_ERR_INVALID, "layer %d: input id", li));
@@ -405,6 +634,10 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             else if (!no_tc && L.group == 1 && tin.cp == 16 && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 && L.dilation_w == 1 &&
                      L.stride_h == L.stride_w && tout.cp <= 256 && !getenv("TB200_NO_GATHER_TC"))
                 kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 160; // 16-channel input: nine 16-byte taps per pixel, five k-steps
+            else if (!no_tc && L.group == 1 && tin.cp == 32 && L.kernel_h == 3 && L.kernel_w == 3 && L.dilation_h == 1 &&
+                     L.dilation_w == 1 && L.stride_h == L.stride_w && (L.stride_h == 1 || L.stride_h == 2) && tout.cp <= 256 &&
+                     !getenv("TB200_NO_GATHER_TC") && !getenv("TB200_NO_WINDOW_CONV"))
+                kind[li] = K_GATHER_TC, wsize = (size_t)tout.cp * 288; // 32-channel input through the window kernel: nine 32-byte taps = nine k-steps
             else if (L.group == C && OC == C && C > 1)
                 kind[li] = K_CONV_DW, wsize = (size_t)L.kernel_h * L.kernel_w * tin.cp;
             else if (!no_tc && L.group == 1 && L.kernel_h == 1 && L.kernel_w == 1 && L.stride_h == 1 && L.stride_w == 1 &&
@@ -450,6 +683,25 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             kind[li] = K_UPSAMPLE;
         else if (L.op == TB200_OP_IDENTITY)
             kind[li] = K_COPY;
+        else if (L.op == TB200_OP_SIGMOID || L.op == TB200_OP_HARDSWISH)
+        {
+            // the reference has no int8 hardswish (hardswish_ref.c:59-66): nothing to be identical to
+            if (L.op == TB200_OP_HARDSWISH && !u8) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: int8 hardswish has no reference kernel", li));
+            kind[li] = K_LUT;
+        }
+        else if (L.op == TB200_OP_SOFTMAX)
+        {
+            if (L.axis != 1) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: softmax axis %d (only the channel axis)", li, L.axis));
+            kind[li] = K_SOFTMAX;
+        }
+        else if (L.op == TB200_OP_RESHAPE)
+        {
+            if (tin.nchw_bytes != tout.nchw_bytes || tin.d.dims[0] != tout.d.dims[0])
+                return bail(fail(TB200_ERR_INVALID, "layer %d: reshape changes the element count or the batch", li));
+            // NHWC(pad) == NCHW order when the tensor is a vector per image or has one channel: a plain copy then
+            const bool same = (H * W == 1 && tout.d.dims[2] * tout.d.dims[3] == 1) || (C == tout.d.dims[1] && H == tout.d.dims[2] && W == tout.d.dims[3]);
+            kind[li] = same ? K_COPY : K_RESHAPE;
+        }
         else
             return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: op %d", li, L.op));
 
@@ -467,6 +719,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             if (u8 && (kind[li] == K_GEMM || kind[li] == K_IGEMM))
                 wtotal += align_up((size_t)(L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w) * tout.cp * 4, 256);
         }
+        if (kind[li] == K_LUT)
+        {
+            blobs[li].w_off = wtotal; // 256-byte table; part of the arena so that it travels with the single broadcast
+            wtotal += 256;
+        }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
             if (g->tensors[L.inputs[k]].input_index >= 0 && kind[li] != K_CONV_STEM && kind[li] != K_STEM_TC && !(kind[li] == K_GATHER_TC && g->tensors[L.inputs[k]].d.dims[1] <= 3)) g->tensors[L.inputs[k]].nhwc_needed = true;
@@ -474,10 +731,91 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
     for (int id : g->output_ids)
         if (g->tensors[id].input_index >= 0) g->tensors[id].nhwc_needed = true;
 
-    // ---- allocate ----
+    // ---- activation arena: one 1 KiB-aligned slot per tensor; a slot is handed on once the tensor's last consumer has run
+    //      (first-fit over a coalescing free list, the role of source/device/cpu/cpu_pool.c:253-439).  Graph inputs and outputs
+    //      keep their slots; with TB200_PRERUN_NO_GRAPH (debug: every intermediate stays readable) nothing is reused. ----
+    std::vector<size_t> scratch_off(num_layers, 0);
+    {
+        const bool reuse = !(flags & TB200_PRERUN_NO_GRAPH) && !getenv("TB200_NO_ARENA_REUSE");
+        for (int li = 0; li < num_layers; li++)
+            for (int k = 0; k < layers[li].num_inputs; k++) g->tensors[layers[li].inputs[k]].last_use = li;
+        struct Blk { size_t off, bytes; };
+        std::vector<Blk> free_list; // sorted by offset
+        size_t top = 0;
+        auto alloc = [&](size_t bytes) -> size_t
+        {
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].bytes >= bytes)
+                {
+                    const size_t off = free_list[i].off;
+                    free_list[i].off += bytes, free_list[i].bytes -= bytes;
+                    if (!free_list[i].bytes) free_list.erase(free_list.begin() + i);
+                    return off;
+                }
+            if (!free_list.empty() && free_list.back().off + free_list.back().bytes == top)
+            {
+                // grow the trailing free block instead of leaving it stranded
+                const size_t off = free_list.back().off;
+                top = off + bytes;
+                free_list.pop_back();
+                return off;
+            }
+            const size_t off = top;
+            top += bytes;
+            return off;
+        };
+        auto release = [&](size_t off, size_t bytes)
+        {
+            if (!reuse || !bytes) return;
+            size_t i = 0;
+            while (i < free_list.size() && free_list[i].off < off) i++;
+            free_list.insert(free_list.begin() + i, Blk{off, bytes});
+            if (i + 1 < free_list.size() && free_list[i].off + free_list[i].bytes == free_list[i + 1].off)
+                free_list[i].bytes += free_list[i + 1].bytes, free_list.erase(free_list.begin() + i + 1);
+            if (i > 0 && free_list[i - 1].off + free_list[i - 1].bytes == free_list[i].off)
+                free_list[i - 1].bytes += free_list[i].bytes, free_list.erase(free_list.begin() + i);
+        };
+        std::vector<char> placed(num_tensors, 0), freed(num_tensors, 0);
+        for (int i = 0; i < num_tensors; i++)
+        {
+            TensorInfo& t = g->tensors[i];
+            g->act_unshared_bytes += t.slot_bytes;
+            if (t.producer < 0 && t.last_use < 0 && t.input_index < 0 && t.output_index < 0)
+            {
+                placed[i] = 1; // neither produced nor read (e.g. the intermediate of a folded node pair): no slot
+                g->act_unshared_bytes -= t.slot_bytes;
+                continue;
+            }
+            if (t.producer < 0) t.off = alloc(t.slot_bytes), placed[i] = 1; // graph inputs
+        }
+        auto permanent = [&](const TensorInfo& t) { return t.input_index >= 0 || t.output_index >= 0 || t.producer < 0; };
+        for (int li = 0; li < num_layers; li++)
+        {
+            const tb200_layer_desc& L = layers[li];
+            if (L.op == TB200_OP_NOP_) continue;
+            TensorInfo& to = g->tensors[L.output];
+            if (!placed[L.output]) to.off = alloc(to.slot_bytes), placed[L.output] = 1;
+            if (kind[li] == K_RESHAPE)
+            {
+                const size_t sb = align_up(to.nchw_bytes, 1024);
+                scratch_off[li] = alloc(sb);
+                g->act_unshared_bytes += sb;
+                release(scratch_off[li], sb);
+            }
+            for (int k = 0; k < L.num_inputs; k++)
+            {
+                const int id = L.inputs[k];
+                TensorInfo& ti = g->tensors[id];
+                if (ti.last_use == li && !permanent(ti) && !freed[id]) release(ti.off, ti.slot_bytes), freed[id] = 1;
+            }
+            if (to.last_use < li && !permanent(to) && !freed[L.output]) release(to.off, to.slot_bytes), freed[L.output] = 1; // dead value
+        }
+        act = top;
+    }
     g->act_bytes = act;
     CUDA_OK(cudaMalloc(&g->act_arena, act ? act : 1024));
-    CUDA_OK(cudaMemsetAsync(g->act_arena, 0, act ? act : 1024, ctx->stream));
+    // pad lanes of every tensor are (re)written by its producer; the initial fill only matters for debugging reads
+    CUDA_OK(cudaMemsetAsync(g->act_arena, (flags & TB200_PRERUN_POISON_ARENA) ? 0xA5 : 0, act ? act : 1024, ctx->stream));
     for (auto& t : g->tensors) t.dev = g->act_arena + t.off;
     g->w_bytes = wtotal ? wtotal : 1024;
     CUDA_OK(cudaMalloc(&g->w_arena, g->w_bytes));
@@ -545,6 +883,12 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         for (int li = 0; li < num_layers; li++)
         {
             const tb200_layer_desc& L = layers[li];
+            if (kind[li] == K_LUT)
+            {
+                build_byte_lut(L.op, g->tensors[L.inputs[0]].d.data_type == TB200_DT_UINT8, g->tensors[L.inputs[0]].d, g->tensors[L.output].d,
+                               img.data() + blobs[li].w_off);
+                continue;
+            }
             if (L.op != TB200_OP_CONV && L.op != TB200_OP_FC) continue;
             const TensorInfo& tin = g->tensors[L.inputs[0]];
             const TensorInfo& tout = g->tensors[L.output];
@@ -575,10 +919,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 }
                 else if (kind[li] == K_GATHER_TC && !(tin.input_index >= 0 && C <= 3))
                 {
-                    // 16-channel NHWC input: k = (kh*3 + kw)*16 + c, 160-byte rows (the last 16 bytes stay 0)
+                    // 16- / 32-channel NHWC input: k = (kh*3 + kw)*Cp + c; rows of 160 bytes (the last 16 stay 0) / 288 bytes
+                    const size_t rowb = tin.cp == 16 ? 160 : 288;
                     for (int o = 0; o < OC; o++)
                         for (int c = 0; c < C; c++)
-                            for (int t = 0; t < 9; t++) dst[(size_t)o * 160 + t * 16 + c] = src[((size_t)o * C + c) * 9 + t];
+                            for (int t = 0; t < 9; t++) dst[(size_t)o * rowb + t * tin.cp + c] = src[((size_t)o * C + c) * 9 + t];
                 }
                 else if (kind[li] == K_STEM_TC || kind[li] == K_GATHER_TC)
                 {
@@ -638,7 +983,9 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 {
                     // the bias term in real units, rounded exactly as the reference rounds it
                     const float S = tin.d.scale * L.weight_scales[0];
-                    fm[2 * o] = (o >= OC) ? 0.f : ((L.recipe == TB200_RECIPE_HCL || fc) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0]);
+                    // FC: fc_ref.c:141-146 multiplies by the BIAS TENSOR's own scale (normally s_in*s_w, but the file decides)
+                    const float Sb = (fc && L.bias_scale != 0.f) ? L.bias_scale : S;
+                    fm[2 * o] = (o >= OC) ? 0.f : (fc ? (float)b[o] * Sb : ((L.recipe == TB200_RECIPE_HCL) ? (float)b[o] * S : ((float)b[o] * tin.d.scale) * L.weight_scales[0]));
                     // tensor-core kinds: corr[oc] = -zx*sum_k w + K*zx*zw (all taps in bounds), carried in the .y lane
                     int32_t corr = 0;
                     if ((tc || kind[li] == K_GATHER_TC) && o < OC)
@@ -697,6 +1044,11 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
         for (int li = 0; li < num_layers; li++)
         {
             const tb200_layer_desc& L = layers[li];
+            if (L.op == TB200_OP_NOP_)
+            {
+                g->layer_kernel[li] = kStepName[K_NONE];
+                continue;
+            }
             TensorInfo& tin = g->tensors[L.inputs[0]];
             TensorInfo& tout = g->tensors[L.output];
             const bool u8 = tin.d.data_type == TB200_DT_UINT8;
@@ -726,6 +1078,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     {
                         g->work_ops += 2.0 * Ntot * OC * C * H * W;
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * C * H * W + (L.bias ? 4.0 * OC : 0);
+                        g->work_wbytes += (double)OC * C * H * W + (L.bias ? 4.0 * OC : 0);
                     }
                 }
                 else
@@ -738,12 +1091,18 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     {
                         g->work_ops += 2.0 * (double)tout.nchw_bytes * k;
                         g->work_bytes += (double)tin.nchw_bytes + tout.nchw_bytes + (double)OC * k + (L.bias ? 4.0 * OC : 0);
+                        g->work_wbytes += (double)OC * k + (L.bias ? 4.0 * OC : 0);
                     }
                 }
                 if (s.kind == K_CONV_STEM || s.kind == K_STEM_TC || (s.kind == K_GATHER_TC && tin.input_index >= 0 && C <= 3))
                     s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
                 s.nhwc16 = (s.kind == K_GATHER_TC && !(tin.input_index >= 0 && C <= 3)) ? 1 : 0;
                 if (s.kind == K_STEM_TC) stem_plan_create(&s.dwp, s.in, s.cs); // falls back to the global-memory gather
+                if (s.kind == K_GATHER_TC)
+                {
+                    window_plan_create(&s.wp, s.in, s.cs, s.nhwc16); // falls back to the global-memory gather (16 channels / NCHW only)
+                    if (!s.wp.valid && s.nhwc16 && tin.cp != 16) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: window plan failed for a 32-channel 3x3 convolution", li));
+                }
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)
                 {
@@ -774,6 +1133,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 p.c = C, p.cp = tin.cp;
                 p.scale0 = tin.d.scale, p.zero0 = tin.d.zero_point, p.out_scale = tout.d.scale, p.out_zero = tout.d.zero_point;
                 p.negative_slope = L.negative_slope;
+                p.post_relu = post_relu[li], p.post_floor4 = (uint32_t)(tout.d.zero_point & 0xff) * 0x01010101u;
                 if (L.op == TB200_OP_RELU)
                     p.mode = 0, p.scale1 = 0, p.zero1 = 0;
                 else
@@ -797,6 +1157,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                     p.in = tdev(tk);
                     p.npix = (long long)N * H * W, p.c = tk.d.dims[1], p.cp_in = tk.cp, p.cp_out = tout.cp, p.c_off = coff;
                     p.s_in = tk.d.scale, p.z_in = tk.d.zero_point, p.s_out = tout.d.scale, p.z_out = tout.d.zero_point;
+                    p.c_write = (k + 1 == L.num_inputs) ? tout.cp - coff : tk.d.dims[1];
                     coff += tk.d.dims[1];
                     if (k + 1 < L.num_inputs) steps.push_back(p);
                     else s = p;
@@ -808,12 +1169,30 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
                 s.n = N, s.h = H, s.w_ = W, s.cp_in = tin.cp, s.scale = L.up_scale;
                 if (OH != H * L.up_scale || OW != W * L.up_scale) return bail(fail(TB200_ERR_INVALID, "layer %d: upsample shape", li));
             }
-            else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT)
+            else if (s.kind == K_LUT)
+            {
+                s.w = g->w_arena + blobs[li].w_off;
+                s.bytes = (long long)(tin.nhwc_bytes / K);
+                s.c = C, s.cp_in = tin.cp;
+                if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: unary op changes the shape", li));
+            }
+            else if (s.kind == K_SOFTMAX)
+            {
+                if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: softmax changes the shape", li));
+                s.npix = (long long)N * H * W, s.c = C, s.cp_in = tin.cp;
+                s.s_in = tin.d.scale, s.z_in = tin.d.zero_point, s.s_out = tout.d.scale, s.z_out = tout.d.zero_point;
+            }
+            else if (s.kind == K_RESHAPE)
+            {
+                s.n = N, s.c = C, s.h = H, s.w_ = W, s.oc_ = OC, s.oh_ = OH, s.ow_ = OW;
+                s.scratch = g->act_arena + scratch_off[li]; // NCHW-ordered bytes of this chunk (chunks never run concurrently)
+            }
+            else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT || L.op == TB200_OP_RESHAPE)
             {
                 s.bytes = (long long)(tin.nhwc_bytes / K);
                 if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));
             }
-            g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : kStepName[s.kind];
+            g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : ((s.kind == K_GATHER_TC && s.wp.valid) ? "conv_window_tcgen05" : kStepName[s.kind]);
             steps.push_back(s);
         }
         for (size_t i = 0; i < g->output_ids.size(); i++)
@@ -835,6 +1214,7 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             if ((rc = build_steps(Kpipe, ck, g->chunk_steps[ck], false)) != 0) return rc;
     }
     g->num_launches = (int)g->steps.size();
+    for (const Step& st : g->steps) g->num_launches += st.kind == K_RESHAPE ? 1 : 0; // two layout kernels
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 
     // ---- capture the launch sequences into CUDA graphs: [0] = whole batch, [1..K] = the pipeline chunks ----
@@ -870,24 +1250,230 @@ extern "C" int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* t
             CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
         }
     }
+    return 0;
+}
+
+// ---- page-locking of the caller's buffers ---------------------------------------------------------------------------------
+// Tengine hands `run` the application's malloc'd NCHW buffers (ir_tensor->data, c_api.c:1141-1160).  A cudaMemcpyAsync from
+// pageable memory is staged by the driver and blocks the calling thread, which would serialise the GPUs of a group and the
+// chunks of the copy/compute pipeline.  So a buffer is registered (cudaHostRegisterPortable) the first time it is seen and the
+// registration is cached (up to 16 ranges, oldest dropped; everything is unregistered at postrun / context destruction).
+// Returns true when [p, p+bytes) is page-locked.  Failure is not an error: the copy then takes the driver's pageable path.
+static bool host_pin(tb200_context* root, const void* ptr, size_t bytes)
+{
+    static const bool off = getenv("TB200_NO_HOST_REGISTER") != nullptr;
+    if (off || !ptr || !bytes) return false;
+    const uint8_t* p = (const uint8_t*)ptr;
+    for (const HostReg& r : root->host_regs)
+        if (p >= r.p && p + bytes <= r.p + r.bytes) return true;
+    for (const void* f : root->host_reg_failed)
+        if (f == ptr) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost)
+    {
+        root->host_regs.push_back(HostReg{p, bytes, false}); // already page-locked by its owner
+        return true;
+    }
+    cudaGetLastError();
+    // an older, smaller registration of the same buffer would make the new one fail: drop overlapping ranges of ours first
+    for (size_t i = 0; i < root->host_regs.size();)
+    {
+        const HostReg& r = root->host_regs[i];
+        if (r.ours && p < r.p + r.bytes && r.p < p + bytes)
+        {
+            if (cudaHostUnregister((void*)r.p) != cudaSuccess) cudaGetLastError();
+            root->host_regs.erase(root->host_regs.begin() + i);
+        }
+        else
+            i++;
+    }
+    if (cudaHostRegister((void*)ptr, bytes, cudaHostRegisterPortable) != cudaSuccess)
+    {
+        cudaGetLastError();
+        if (root->host_reg_failed.size() < 64) root->host_reg_failed.push_back(ptr);
+        return false;
+    }
+    root->host_regs.push_back(HostReg{p, bytes, true});
+    if (root->host_regs.size() > 16)
+    {
+        if (root->host_regs[0].ours && cudaHostUnregister((void*)root->host_regs[0].p) != cudaSuccess) cudaGetLastError();
+        root->host_regs.erase(root->host_regs.begin());
+    }
+    return true;
+}
+
+// every shard of a graph, the root's own first
+template <typename F>
+static int for_each_shard(tb200_graph* g, F f)
+{
+    int rc = f(g, 0);
+    for (size_t i = 0; rc == 0 && i < g->shards.size(); i++) rc = f(g->shards[i], (int)i + 1);
+    return rc;
+}
+static inline size_t image_bytes(const tb200_graph* g, int tensor_id) { return g->tensors[tensor_id].nchw_bytes / (size_t)g->num_images; }
+
+// One ncclBroadcast of the packed arena from GPU 0 to every other GPU of the group (grouped: one call per device from this
+// single thread), or peer copies when NCCL is not in use.
+static int broadcast_arena(tb200_graph* g)
+{
+    tb200_context* root = g->ctx;
+    if (g->shards.empty()) return 0;
+    CUDA_OK(cudaSetDevice(root->device));
+    CUDA_OK(cudaStreamSynchronize(root->stream));
+    NcclApi* nc = root->comms.empty() ? nullptr : nccl_api();
+    if (nc)
+    {
+        int r = nc->GroupStart();
+        if (r == 0) r = nc->Broadcast(g->w_arena, g->w_arena, g->w_bytes, /*ncclUint8*/ 1, 0, root->comms[0], root->stream);
+        for (size_t i = 0; r == 0 && i < g->shards.size(); i++)
+        {
+            tb200_graph* sh = g->shards[i];
+            if (sh->w_bytes != g->w_bytes) return fail(TB200_ERR_INVALID, "shard %d planned a different weight arena (%zu vs %zu bytes)", (int)i + 1, sh->w_bytes, g->w_bytes);
+            r = nc->Broadcast(sh->w_arena, sh->w_arena, sh->w_bytes, 1, 0, root->comms[i + 1], sh->ctx->stream);
+        }
+        const int r2 = nc->GroupEnd();
+        if (r || r2) return fail(TB200_ERR_CUDA, "ncclBroadcast of the weight arena failed: %s", nc->GetErrorString(r ? r : r2));
+    }
+    else
+    {
+        for (size_t i = 0; i < g->shards.size(); i++)
+        {
+            tb200_graph* sh = g->shards[i];
+            if (sh->w_bytes != g->w_bytes) return fail(TB200_ERR_INVALID, "shard %d planned a different weight arena", (int)i + 1);
+            CUDA_OK(cudaMemcpyPeerAsync(sh->w_arena, sh->ctx->device, g->w_arena, root->device, g->w_bytes, root->stream));
+        }
+    }
+    CUDA_OK(cudaSetDevice(root->device));
+    CUDA_OK(cudaStreamSynchronize(root->stream));
+    for (tb200_graph* sh : g->shards)
+    {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        CUDA_OK(cudaStreamSynchronize(sh->ctx->stream));
+    }
+    CUDA_OK(cudaSetDevice(root->device));
+    return 0;
+}
+
+static int prerun_guarded(tb200_context* ctx, const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers, int num_layers,
+                          const int32_t* input_ids, int num_inputs, const int32_t* output_ids, int num_outputs, int flags, tb200_graph** out)
+{
+    tb200_graph* g = new tb200_graph();
+    g->ctx = ctx, g->flags = flags;
+    const int rc = prerun_one(ctx, tensors, num_tensors, layers, num_layers, input_ids, num_inputs, output_ids, num_outputs, flags, g);
+    if (rc)
+    {
+        // a failed CUDA call may have left a capture open on the context stream
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ctx->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+        {
+            cudaGraph_t junk = nullptr;
+            cudaStreamEndCapture(ctx->stream, &junk);
+            if (junk) cudaGraphDestroy(junk);
+        }
+        cudaGetLastError();
+        destroy_graph(g);
+        return rc;
+    }
+    g->num_images = g->total_images = tensors[0].dims[0];
     *out = g;
     return 0;
 }
 
 extern "C" {
 
-int tb200_graph_upload(tb200_graph* g, int input_index, const void* host_nchw)
+int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers, int num_layers,
+                       const int32_t* input_ids, int num_inputs, const int32_t* output_ids, int num_outputs, int flags, tb200_graph** out)
 {
-    if (!g || input_index < 0 || input_index >= (int)g->input_ids.size() || !host_nchw) return fail(TB200_ERR_INVALID, "bad upload arguments");
-    CUDA_OK(cudaSetDevice(g->ctx->device));
-    CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[input_index], host_nchw, g->tensors[g->input_ids[input_index]].nchw_bytes,
-                            cudaMemcpyHostToDevice, g->ctx->stream));
+    if (!ctx || !tensors || !layers || !out || num_tensors <= 0 || num_layers <= 0) return fail(TB200_ERR_INVALID, "bad arguments");
+    if ((num_inputs > 0 && !input_ids) || (num_outputs > 0 && !output_ids)) return fail(TB200_ERR_INVALID, "null id table");
+    // ---- how many GPUs take part: the batch (dim 0, the same for every tensor) is cut into contiguous slices ----
+    int R = 1 + (int)ctx->peers.size();
+    const int N = tensors[0].dims[0];
+    for (int i = 0; i < num_tensors; i++)
+        if (tensors[i].dims[0] != N) R = 1; // not a plain batch dimension: GPU 0 runs the whole subgraph
+    if (R > N) R = N > 0 ? N : 1;
+    if (R == 1) return prerun_guarded(ctx, tensors, num_tensors, layers, num_layers, input_ids, num_inputs, output_ids, num_outputs, flags, out);
+
+    std::vector<tb200_tensor_desc> td(tensors, tensors + num_tensors);
+    tb200_graph* root = nullptr;
+    int first = 0;
+    for (int r = 0; r < R; r++)
+    {
+        const int count = N / R + (r < N % R ? 1 : 0);
+        for (auto& t : td) t.dims[0] = count;
+        tb200_graph* sh = nullptr;
+        tb200_context* c = r == 0 ? ctx : ctx->peers[r - 1];
+        // GPU 0 packs the weights; the others only allocate the arena (same layout: it depends on the descriptors alone)
+        const int rc = prerun_guarded(c, td.data(), num_tensors, layers, num_layers, input_ids, num_inputs, output_ids, num_outputs,
+                                      flags | (r ? TB200_PRERUN_NO_WEIGHTS : 0), &sh);
+        if (rc)
+        {
+            if (root) destroy_graph(root);
+            cudaSetDevice(ctx->device);
+            return rc;
+        }
+        sh->first_image = first, sh->num_images = count, sh->total_images = N;
+        first += count;
+        if (r == 0) root = sh;
+        else root->shards.push_back(sh);
+    }
+    if (!(flags & TB200_PRERUN_NO_WEIGHTS))
+    {
+        const int rc = broadcast_arena(root);
+        if (rc)
+        {
+            destroy_graph(root);
+            return rc;
+        }
+    }
+    cudaSetDevice(ctx->device);
+    *out = root;
     return 0;
 }
 
-int tb200_graph_launch(tb200_graph* g)
+int tb200_graph_broadcast_weights(tb200_graph* g)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
+    return broadcast_arena(g);
+}
+
+int tb200_graph_num_shards(tb200_graph* g) { return g ? 1 + (int)g->shards.size() : 0; }
+
+int tb200_graph_shard(tb200_graph* g, int index, int* cuda_device, int* first_image, int* num_images)
+{
+    if (!g || index < 0 || index > (int)g->shards.size()) return fail(TB200_ERR_INVALID, "shard index out of range");
+    const tb200_graph* sh = index == 0 ? g : g->shards[index - 1];
+    if (cuda_device) *cuda_device = sh->ctx->device;
+    if (first_image) *first_image = sh->first_image;
+    if (num_images) *num_images = sh->num_images;
+    return 0;
+}
+
+int tb200_graph_arena_bytes(tb200_graph* g, size_t* activation_bytes, size_t* unshared_bytes, size_t* weight_bytes)
+{
+    if (!g) return fail(TB200_ERR_INVALID, "null graph");
+    if (activation_bytes) *activation_bytes = g->act_bytes;
+    if (unshared_bytes) *unshared_bytes = g->act_unshared_bytes;
+    if (weight_bytes) *weight_bytes = g->w_bytes;
+    return 0;
+}
+
+int tb200_graph_upload(tb200_graph* g, int input_index, const void* host_nchw)
+{
+    if (!g || input_index < 0 || input_index >= (int)g->input_ids.size() || !host_nchw) return fail(TB200_ERR_INVALID, "bad upload arguments");
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        const int id = sh->input_ids[input_index];
+        CUDA_OK(cudaMemcpyAsync(sh->in_nchw_dev[input_index], (const uint8_t*)host_nchw + (size_t)sh->first_image * image_bytes(sh, id),
+                                sh->tensors[id].nchw_bytes, cudaMemcpyHostToDevice, sh->ctx->stream));
+        return 0;
+    });
+    cudaSetDevice(g->ctx->device);
+    return rc;
+}
+
+static int launch_one(tb200_graph* g)
+{
     CUDA_OK(cudaSetDevice(g->ctx->device));
     if (!g->cu_execs.empty())
     {
@@ -902,57 +1488,91 @@ int tb200_graph_launch(tb200_graph* g)
     return 0;
 }
 
+int tb200_graph_launch(tb200_graph* g)
+{
+    if (!g) return fail(TB200_ERR_INVALID, "null graph");
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) { return launch_one(sh); });
+    cudaSetDevice(g->ctx->device);
+    return rc;
+}
+
 int tb200_graph_download(tb200_graph* g, int output_index, void* host_nchw)
 {
     if (!g || output_index < 0 || output_index >= (int)g->output_ids.size() || !host_nchw) return fail(TB200_ERR_INVALID, "bad download arguments");
-    CUDA_OK(cudaSetDevice(g->ctx->device));
-    CUDA_OK(cudaMemcpyAsync(host_nchw, g->out_nchw_dev[output_index], g->tensors[g->output_ids[output_index]].nchw_bytes,
-                            cudaMemcpyDeviceToHost, g->ctx->stream));
-    return 0;
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        const int id = sh->output_ids[output_index];
+        CUDA_OK(cudaMemcpyAsync((uint8_t*)host_nchw + (size_t)sh->first_image * image_bytes(sh, id), sh->out_nchw_dev[output_index],
+                                sh->tensors[id].nchw_bytes, cudaMemcpyDeviceToHost, sh->ctx->stream));
+        return 0;
+    });
+    cudaSetDevice(g->ctx->device);
+    return rc;
 }
 
 int tb200_graph_sync(tb200_graph* g)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
-    CUDA_OK(cudaStreamSynchronize(g->ctx->stream));
-    return 0;
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        CUDA_OK(cudaStreamSynchronize(sh->ctx->stream));
+        return 0;
+    });
+    cudaSetDevice(g->ctx->device);
+    return rc;
 }
 
-int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const* host_outputs)
+// ---- run: three phases over the shards so that every GPU's copy engine starts before any GPU's kernels are queued ----
+// (1) queue the H2D copies of all chunks on the shard's copy stream
+static int run_enqueue_h2d(tb200_graph* g, const void* const* host_inputs)
 {
-    if (!g || !host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "bad run arguments");
-    int rc;
-    if (!host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "run: null buffer table");
-    for (size_t i = 0; i < g->input_ids.size(); i++)
-        if (!host_inputs[i]) return fail(TB200_ERR_INVALID, "run: input %d has no host buffer", (int)i);
-    for (size_t i = 0; i < g->output_ids.size(); i++)
-        if (!host_outputs[i]) return fail(TB200_ERR_INVALID, "run: output %d has no host buffer (the graph has %d outputs)", (int)i, (int)g->output_ids.size());
+    CUDA_OK(cudaSetDevice(g->ctx->device));
     if (g->chunks <= 1 || g->cu_execs.empty())
     {
         for (size_t i = 0; i < g->input_ids.size(); i++)
-            if ((rc = tb200_graph_upload(g, (int)i, host_inputs[i])) != 0) return rc;
-        if ((rc = tb200_graph_launch(g)) != 0) return rc;
-        for (size_t i = 0; i < g->output_ids.size(); i++)
-            if ((rc = tb200_graph_download(g, (int)i, host_outputs[i])) != 0) return rc;
-        return tb200_graph_sync(g);
+        {
+            const int id = g->input_ids[i];
+            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i], (const uint8_t*)host_inputs[i] + (size_t)g->first_image * image_bytes(g, id),
+                                    g->tensors[id].nchw_bytes, cudaMemcpyHostToDevice, g->ctx->stream));
+        }
+        return 0;
     }
     // Pipelined: the H2D copies of all chunks are queued back to back on the copy stream (the link stays busy), chunk k's
     // kernels start as soon as ITS slice has landed, and its outputs leave on a third stream while chunk k+1 computes.
-    CUDA_OK(cudaSetDevice(g->ctx->device));
     const int K = g->chunks;
-    cudaStream_t cs = g->ctx->stream;
-    CUDA_OK(cudaEventRecord(g->ev_done, cs)); // order after whatever the caller queued on the context stream
+    CUDA_OK(cudaEventRecord(g->ev_done, g->ctx->stream)); // order after whatever the caller queued on the context stream
     CUDA_OK(cudaStreamWaitEvent(g->copy_stream, g->ev_done, 0));
     for (int ck = 0; ck < K; ck++)
     {
         for (size_t i = 0; i < g->input_ids.size(); i++)
         {
-            const size_t bytes = g->tensors[g->input_ids[i]].nchw_bytes / K;
-            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i] + ck * bytes, (const uint8_t*)host_inputs[i] + ck * bytes, bytes, cudaMemcpyHostToDevice,
-                                    g->copy_stream));
+            const int id = g->input_ids[i];
+            const size_t bytes = g->tensors[id].nchw_bytes / K;
+            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i] + ck * bytes, (const uint8_t*)host_inputs[i] + (size_t)g->first_image * image_bytes(g, id) + ck * bytes,
+                                    bytes, cudaMemcpyHostToDevice, g->copy_stream));
         }
         CUDA_OK(cudaEventRecord(g->ev_in[ck], g->copy_stream));
     }
+    return 0;
+}
+// (2) kernels + D2H
+static int run_enqueue_compute(tb200_graph* g, void* const* host_outputs)
+{
+    CUDA_OK(cudaSetDevice(g->ctx->device));
+    cudaStream_t cs = g->ctx->stream;
+    if (g->chunks <= 1 || g->cu_execs.empty())
+    {
+        int rc = launch_one(g);
+        if (rc) return rc;
+        for (size_t i = 0; i < g->output_ids.size(); i++)
+        {
+            const int id = g->output_ids[i];
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + (size_t)g->first_image * image_bytes(g, id), g->out_nchw_dev[i], g->tensors[id].nchw_bytes,
+                                    cudaMemcpyDeviceToHost, cs));
+        }
+        return 0;
+    }
+    const int K = g->chunks;
     for (int ck = 0; ck < K; ck++)
     {
         CUDA_OK(cudaStreamWaitEvent(cs, g->ev_in[ck], 0));
@@ -961,22 +1581,53 @@ int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const*
         CUDA_OK(cudaStreamWaitEvent(g->d2h_stream, g->ev_out[ck], 0));
         for (size_t i = 0; i < g->output_ids.size(); i++)
         {
-            const size_t bytes = g->tensors[g->output_ids[i]].nchw_bytes / K;
-            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + ck * bytes, g->out_nchw_dev[i] + ck * bytes, bytes, cudaMemcpyDeviceToHost,
-                                    g->d2h_stream));
+            const int id = g->output_ids[i];
+            const size_t bytes = g->tensors[id].nchw_bytes / K;
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + (size_t)g->first_image * image_bytes(g, id) + ck * bytes, g->out_nchw_dev[i] + ck * bytes, bytes,
+                                    cudaMemcpyDeviceToHost, g->d2h_stream));
         }
     }
-    CUDA_OK(cudaStreamSynchronize(g->d2h_stream));
-    CUDA_OK(cudaStreamSynchronize(cs));
     return 0;
+}
+// (3) wait
+static int run_wait(tb200_graph* g)
+{
+    CUDA_OK(cudaSetDevice(g->ctx->device));
+    if (g->d2h_stream && g->chunks > 1 && !g->cu_execs.empty()) CUDA_OK(cudaStreamSynchronize(g->d2h_stream));
+    CUDA_OK(cudaStreamSynchronize(g->ctx->stream));
+    return 0;
+}
+
+int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const* host_outputs)
+{
+    if (!g || !host_inputs || !host_outputs) return fail(TB200_ERR_INVALID, "bad run arguments");
+    for (size_t i = 0; i < g->input_ids.size(); i++)
+        if (!host_inputs[i]) return fail(TB200_ERR_INVALID, "run: input %d has no host buffer", (int)i);
+    for (size_t i = 0; i < g->output_ids.size(); i++)
+        if (!host_outputs[i]) return fail(TB200_ERR_INVALID, "run: output %d has no host buffer (the graph has %d outputs)", (int)i, (int)g->output_ids.size());
+    // page-lock the caller's buffers (whole batch) on first sight
+    CUDA_OK(cudaSetDevice(g->ctx->device));
+    for (size_t i = 0; i < g->input_ids.size(); i++) host_pin(g->ctx, host_inputs[i], image_bytes(g, g->input_ids[i]) * (size_t)g->total_images);
+    for (size_t i = 0; i < g->output_ids.size(); i++) host_pin(g->ctx, host_outputs[i], image_bytes(g, g->output_ids[i]) * (size_t)g->total_images);
+    int rc = for_each_shard(g, [&](tb200_graph* sh, int) { return run_enqueue_h2d(sh, host_inputs); });
+    if (!rc) rc = for_each_shard(g, [&](tb200_graph* sh, int) { return run_enqueue_compute(sh, host_outputs); });
+    const int rc2 = for_each_shard(g, [&](tb200_graph* sh, int) { return run_wait(sh); }); // always drain what was queued
+    cudaSetDevice(g->ctx->device);
+    return rc ? rc : rc2;
 }
 
 int tb200_graph_postrun(tb200_graph* g)
 {
     if (!g) return 0;
-    cudaSetDevice(g->ctx->device);
-    cudaStreamSynchronize(g->ctx->stream);
+    for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        cudaSetDevice(sh->ctx->device);
+        cudaStreamSynchronize(sh->ctx->stream);
+        return 0;
+    });
+    host_unregister_all(g->ctx); // the application may free its buffers after postrun_graph()
+    tb200_context* root = g->ctx;
     destroy_graph(g);
+    cudaSetDevice(root->device);
     return 0;
 }
 
@@ -987,7 +1638,13 @@ int tb200_graph_weight_arena(tb200_graph* g, void** device_ptr, size_t* bytes)
     return 0;
 }
 
-int tb200_graph_num_launches(tb200_graph* g) { return g ? g->num_launches : 0; }
+int tb200_graph_num_launches(tb200_graph* g)
+{
+    if (!g) return 0;
+    int n = g->num_launches;
+    for (tb200_graph* sh : g->shards) n += sh->num_launches;
+    return n;
+}
 
 const char* tb200_graph_layer_kernel(tb200_graph* g, int layer)
 {
@@ -998,48 +1655,59 @@ const char* tb200_graph_layer_kernel(tb200_graph* g, int layer)
 int tb200_graph_read_tensor(tb200_graph* g, int tensor_id, void* host_nchw)
 {
     if (!g || tensor_id < 0 || tensor_id >= (int)g->tensors.size() || !host_nchw) return fail(TB200_ERR_INVALID, "bad arguments");
-    CUDA_OK(cudaSetDevice(g->ctx->device));
-    const TensorInfo& t = g->tensors[tensor_id];
-    uint8_t* tmp = nullptr;
-    CUDA_OK(cudaMalloc(&tmp, t.nchw_bytes));
-    const uint8_t* src = t.dev;
-    cudaError_t e = launch_nhwc_to_nchw(src, tmp, t.d.dims[0], t.d.dims[1], t.d.dims[2], t.d.dims[3], g->ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(host_nchw, tmp, t.nchw_bytes, cudaMemcpyDeviceToHost, g->ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(tmp);
-    if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "read_tensor: %s", cudaGetErrorString(e));
-    return 0;
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        const TensorInfo& t = sh->tensors[tensor_id];
+        uint8_t* tmp = nullptr;
+        CUDA_OK(cudaMalloc(&tmp, t.nchw_bytes));
+        cudaError_t e = launch_nhwc_to_nchw(t.dev, tmp, t.d.dims[0], t.d.dims[1], t.d.dims[2], t.d.dims[3], sh->ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((uint8_t*)host_nchw + (size_t)sh->first_image * image_bytes(sh, tensor_id), tmp, t.nchw_bytes, cudaMemcpyDeviceToHost, sh->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sh->ctx->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "read_tensor: %s", cudaGetErrorString(e));
+        return 0;
+    });
+    cudaSetDevice(g->ctx->device);
+    return rc;
 }
 
 int tb200_graph_profile(tb200_graph* g, float* layer_ms, int num_layers)
 {
     if (!g || !layer_ms || num_layers < (int)g->layers.size()) return fail(TB200_ERR_INVALID, "bad arguments");
-    CUDA_OK(cudaSetDevice(g->ctx->device));
+    CUDA_OK(cudaSetDevice(g->ctx->device)); // the shard of GPU 0 (every shard runs the same launch sequence on its slice)
     for (int i = 0; i < num_layers; i++) layer_ms[i] = 0.f;
     cudaEvent_t a, b;
     CUDA_OK(cudaEventCreate(&a));
     CUDA_OK(cudaEventCreate(&b));
+    int rc = 0;
     for (const Step& s : g->steps)
     {
         cudaEventRecord(a, g->ctx->stream);
-        int rc = run_step(g, s, g->ctx->stream);
+        rc = run_step(g, s, g->ctx->stream);
         cudaEventRecord(b, g->ctx->stream);
-        if (rc) return rc;
-        CUDA_OK(cudaEventSynchronize(b));
+        if (rc) break;
+        if (cudaEventSynchronize(b) != cudaSuccess)
+        {
+            rc = fail(TB200_ERR_CUDA, "profile: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, a, b);
         if (s.layer >= 0) layer_ms[s.layer] += ms;
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    return 0;
+    return rc;
 }
 
 int tb200_graph_work(tb200_graph* g, double* ops, double* bytes)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
-    if (ops) *ops = g->work_ops;
-    if (bytes) *bytes = g->work_bytes;
+    double o = g->work_ops, b = g->work_bytes;
+    for (tb200_graph* sh : g->shards) o += sh->work_ops, b += sh->work_bytes - sh->work_wbytes; // weights count once per launch
+    if (ops) *ops = o;
+    if (bytes) *bytes = b;
     return 0;
 }
 
@@ -1051,6 +1719,7 @@ static EpiParams epi_from_abi(const tb200k_epilogue* e)
     p.in_zero = e->in_zero, p.w_zero = e->w_zero, p.out_zero = e->out_zero, p.activation = e->activation, p.recipe = e->recipe;
     p.is_uint8 = e->is_uint8, p.fc_rounding = e->fc_rounding, p.has_bias = e->bias != nullptr;
     p.in_w_scale = e->in_scale * e->w_scale_tensor;
+    p.bias_scale = p.in_w_scale;
     p.fast_ok = 0; // the raw kernel entry points always use the literal reference arithmetic
     return p;
 }

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
+#include "tc_common.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -36,7 +37,7 @@ namespace tb200 {
 #define TLOG_E(tag) do { } while (0)
 #endif
 
-static constexpr int BLOCK_M = 128;
+
 static constexpr int EPI_WARPS = 16; // four per TMEM lane quarter
 static constexpr int EPI_THREADS = EPI_WARPS * 32;
 static constexpr int GEMM_THREADS = 64 + EPI_THREADS;
@@ -47,33 +48,6 @@ static constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 static constexpr int PAR_MAX = 2048; // channels whose epilogue constants stay resident in smem for the whole kernel
 static constexpr int MAX_STAGES = 24;
 static constexpr int B_RESIDENT_MAX = 96 * 1024; // weights of the CTA's N tile stay in smem when they fit in this many bytes
-
-// K-major operand tile in shared memory, rows of `swizzle` bytes, 8-row groups `8*swizzle` bytes apart
-// (cute/atom/mma_traits_sm100.hpp: canonical layout ((8,n),2):((swizzle/16,SBO),1), LBO = 1, version 1).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int swizzle)
-{
-    const uint64_t layout = (swizzle == 128) ? 2ull : (swizzle == 64) ? 4ull : 6ull;
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(((8 * swizzle) >> 4) & 0x3fff) << 32; // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-    d |= layout << 61;
-    return d;
-}
-
-// UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): S32 accumulate, A/B int8 or uint8,
-// both K-major, M = 128, N = block_n.
-__host__ __device__ inline uint32_t make_idesc_i8(int block_n, bool a_signed, bool b_signed)
-{
-    uint32_t d = 0;
-    d |= 2u << 4;                        // c_format = S32
-    d |= (a_signed ? 1u : 0u) << 7;      // a_format
-    d |= (b_signed ? 1u : 0u) << 10;     // b_format
-    d |= (uint32_t)(block_n >> 3) << 17; // n_dim
-    d |= (uint32_t)(BLOCK_M >> 4) << 24; // m_dim
-    return d;
-}
 
 struct GemmArgs
 {
@@ -170,57 +144,95 @@ __device__ __forceinline__ void epilogue_unit_exact(const uint32_t (&v)[16], uin
 // uint8 flavour: v = sum x*w over in-bounds taps (raw bytes), sx = sum x.  The true accumulator is
 //   sum (x-zx)(w-zw) = v - zw*sx + corr[oc] + sum_{padding taps t} btab[t][oc]
 // with corr[oc] = -zx*sum_k w + taps*Cin*zx*zw (interior pixels) folded into the per-channel constants.
+// border pixel: sum of the per-tap corrections of the taps that fell into the padding, for one channel (rare rows; a call, so
+// that the hot path carries neither the loop nor an addressable accumulator array)
+__device__ __noinline__ int32_t u8_border_correction(uint64_t pad_mask, const int32_t* __restrict__ btab, int taps, int ocp, int oc)
+{
+    int32_t c = 0;
+    if (oc < ocp)
+        for (int t = 0; t < taps; t++)
+            if ((pad_mask >> t) & 1ull) c += __ldg(btab + (size_t)t * ocp + oc);
+    return c;
+}
+
 template <bool EXACT>
 __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_t sx, uint64_t pad_mask, const GemmArgs& g, uint32_t par_addr,
                                                  uint32_t dst_addr, int oc0, const EpiParams& e)
 {
     const int32_t rowc = -e.w_zero * sx;
-    int32_t a[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) a[k] = (int32_t)v[k] + rowc;
-    if (pad_mask)
-    {
-        // border pixel: add the per-tap corrections of the taps that fell into the padding (rare rows)
-        for (int t = 0; t < g.taps; t++)
-            if ((pad_mask >> t) & 1ull)
-            {
-                const int32_t* bt = g.btab + (size_t)t * g.ocp + oc0;
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                    if (oc0 + k < g.ocp) a[k] += __ldg(bt + k);
-            }
-    }
     uint32_t w[4];
     if (!EXACT)
     {
-        // (the packed requant_unit16_u8 of the gather kernel was measured SLOWER here, with and without the TMEM prefetch:
-        //  8.0 vs 6.7 ms for ResNet-50 uint8's 1x1 layers)
-        uint32_t bad = 0;
+        // Packed form (common.cuh requant_fast8_u8), eight channels at a time so that the live set stays below the 96-register
+        // cap of this 18-warp kernel: true accumulator = v + rowc + corr[oc] (one IADD3 per element), then the float chain on the
+        // FMA pipe as FMUL2 / FADD2 pairs, clip + zero point + saturation as one DPX op per pair.
+        float gw[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int h = 0; h < 2; h++)
         {
-            const float4 p01 = lds_f4(par_addr + j * 32);
-            const float4 p23 = lds_f4(par_addr + j * 32 + 16);
-            const float m4[4] = {p01.x, p01.z, p23.x, p23.z};
-            // corr[oc] travels in the .y lanes
-            a[j * 4 + 0] += __float_as_int(p01.y), a[j * 4 + 1] += __float_as_int(p01.w);
-            a[j * 4 + 2] += __float_as_int(p23.y), a[j * 4 + 3] += __float_as_int(p23.w);
-            const int32_t a4[4] = {a[j * 4], a[j * 4 + 1], a[j * 4 + 2], a[j * 4 + 3]};
-            w[j] = requant_fast4_u8(a4, e, m4, bad, 1u << (4 * j));
+            int32_t a8[8];
+            float b8[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const float4 p = lds_f4(par_addr + h * 64 + k * 16); // (bias term, corr) of channels 2k, 2k+1 of this half
+                a8[2 * k] = (int32_t)v[h * 8 + 2 * k] + rowc + __float_as_int(p.y);
+                a8[2 * k + 1] = (int32_t)v[h * 8 + 2 * k + 1] + rowc + __float_as_int(p.w);
+                b8[2 * k] = p.x, b8[2 * k + 1] = p.z;
+            }
+            if (pad_mask)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; k++) a8[k] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + h * 8 + k);
+            }
+            requant_fast8_u8(a8, b8, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
         }
-        // pad lanes of uint8 tensors hold 0, not the zero point
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            if (oc0 + k >= g.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3))), bad &= ~(1u << k);
-        if (bad)
+        if (e.q_byte_add)
         {
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
+        }
+        if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
+        {
+            // rare (2.4e-4 of the elements): exact recomputation of the guarded words from the raw accumulators
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (gw[j] > 0.5f - TB200_TIE_EPS)
+                {
+                    int32_t a4[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                    {
+                        const float2 pp = lds_f2(par_addr + (j * 4 + t) * 8);
+                        a4[t] = (int32_t)v[j * 4 + t] + rowc + __float_as_int(pp.y);
+                    }
+                    if (pad_mask)
+                    {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) a4[t] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + j * 4 + t);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++) w[j] = requant_fix_byte(w[j], t, a4[t], oc0 + j * 4 + t, e);
+                }
+        }
+        if (oc0 + 16 > g.oc)
+        {
+            // pad lanes of uint8 tensors hold 0, not the zero point
 #pragma unroll
             for (int k = 0; k < 16; k++)
-                if ((bad >> k) & 1u) w[k >> 2] = requant_fix_byte(w[k >> 2], k & 3, a[k], oc0 + k, e);
+                if (oc0 + k >= g.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3)));
         }
     }
     else
     {
+        int32_t a[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[k] = (int32_t)v[k] + rowc;
+        if (pad_mask)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + k);
+        }
 #pragma unroll
         for (int k = 0; k < 16; k++)
         {
@@ -596,37 +608,6 @@ struct StemArgs
     int tiles_w, tiles_h, box_w, box_h, in_bytes; // TMA-staged input window (16 x 8 output pixels per tile)
     int xoff; // the window starts xoff bytes left of the first tap: the innermost TMA coordinate must be 16-byte aligned
 };
-
-template <bool FUSE>
-__device__ __forceinline__ void stem_unit_fast(const uint32_t (&v)[16], uint32_t par_addr, int oc0, const EpiParams& e, uint32_t (&w)[4])
-{
-    float gw[4];
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-    {
-        float4 p[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) p[k] = lds_f4(par_addr + h * 64 + k * 16);
-        const int32_t a8[8] = {(int32_t)v[h * 8], (int32_t)v[h * 8 + 1], (int32_t)v[h * 8 + 2], (int32_t)v[h * 8 + 3],
-                               (int32_t)v[h * 8 + 4], (int32_t)v[h * 8 + 5], (int32_t)v[h * 8 + 6], (int32_t)v[h * 8 + 7]};
-        requant_fast8_i8<FUSE>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
-    }
-    if (e.q_byte_add)
-    {
-#pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
-    }
-    if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
-    {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (gw[j] > 0.5f - TB200_TIE_EPS)
-                w[j] = requant_fix_word<FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, e);
-    }
-}
-
-// row r, 16-byte chunk c16 of a SW32 K-major tile (8-row groups of 256 bytes, chunk index ^= bit 2 of the row)
-__device__ __forceinline__ uint32_t sw32_offset(int r, int c16) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 32 + ((c16 ^ ((r >> 2) & 1)) << 4)); }
 
 // TMA_IN: the input window of the tile (3 channel planes x box_h rows x box_w bytes, zero-filled outside the image) is
 // staged in shared memory by one 4-D TMA load, double-buffered; the gather is then 27 unpredicated LDS.U8 + IMAD per

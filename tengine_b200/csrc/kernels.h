@@ -31,6 +31,8 @@ struct PointwiseParams
     float scale0, scale1, out_scale;
     int zero0, zero1, out_zero;
     float negative_slope;
+    int post_relu;        // a same-scale ReLU node folded into this eltwise: bytes = max(bytes, zero point)
+    uint32_t post_floor4; // uint8: the output zero point replicated x4
 };
 
 cudaError_t launch_conv_direct(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
@@ -38,8 +40,13 @@ cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvS
 cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
 cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st);
 cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long bytes, const PointwiseParams& p, bool u8, cudaStream_t st);
-cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int c_write, int cp_in, int cp_out, int c_off, float s_in,
                                int z_in, float s_out, int z_out, bool u8, cudaStream_t st);
+// unary byte ops (sigmoid, hardswish) as a 256-entry table built at prerun; pad lanes (channel >= c) stay 0
+cudaError_t launch_byte_lut(const void* in, void* out, const uint8_t* lut, long long bytes, int c, int cp, cudaStream_t st);
+// softmax over the channel axis (softmax_kernel_ref_int8.c / _uint8.c), one thread per pixel
+cudaError_t launch_softmax(const void* in, void* out, long long npix, int c, int cp, float s_in, int z_in, float s_out, int z_out, bool u8,
+                           cudaStream_t st);
 cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st);
 cudaError_t launch_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
 cudaError_t launch_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
@@ -53,6 +60,17 @@ struct DwPlan
 };
 int dw_plan_create(DwPlan* plan, const void* in, const ConvShape& s, const EpiParams& e);
 cudaError_t launch_conv_dw_tma(const DwPlan& plan, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
+
+// ---- small-Cin convolutions with a TMA-staged input window (conv_window.cu) -----------------------------------
+struct WindowPlan
+{
+    alignas(64) unsigned char tmap_in[128]; // CUtensorMap over the input: NCHW (W, H, C, N) or NHWC (Cp, W, H, N)
+    int valid;
+    int layout; // 0 NCHW 3x3, 1 NCHW 7x7, 2 NHWC 16 B/pixel 3x3, 3 NHWC 32 B/pixel 3x3
+    int box_w, box_h, xoff, in_bytes, ks, smem_bytes;
+};
+int window_plan_create(WindowPlan* plan, const void* in, const ConvShape& s, int nhwc); // < 0: not applicable
+cudaError_t launch_conv_window(const WindowPlan& plan, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
 
 // ---- tcgen05 GEMM (gemm_tcgen05.cu) ------------------------------------------------------------------
 // out[M][ldo] (bytes) = requant( A[M][K] (row pitch lda bytes) . B[OCp][K]^T )

@@ -309,6 +309,15 @@ __global__ void __launch_bounds__(128, (OCT == 32 && !U8) ? 4 : 2)
 __device__ __forceinline__ int clamp_i8(int q) { return (q > 127 ? 127 : (q < -127 ? -127 : q)) & 0xff; }
 __device__ __forceinline__ int clamp_u8(int q) { return q > 255 ? 255 : (q < 0 ? 0 : q); }
 
+// A ReLU node whose output has its input's quantisation, folded into the eltwise that feeds it (engine.cu planner): on the
+// requantised bytes it is max(byte, zero point) / max(byte, 0) -- see relu_same_scale_kernel.  uint8 only without pad lanes.
+#define POINTWISE_POST_RELU(wo)                                                                            \
+    if (p.post_relu)                                                                                       \
+    {                                                                                                      \
+        _Pragma("unroll") for (int w_ = 0; w_ < 4; w_++)                                                   \
+            (wo)[w_] = U8 ? __vmaxu4((wo)[w_], p.post_floor4) : __vmaxs4((wo)[w_], 0u);                    \
+    }
+
 // pooling/pooling_kernel_ref_int8.c:84-189, pooling_kernel_ref_uint8.c:91-204. Thread = pixel x 4 channels.
 template <bool U8>
 __global__ void __launch_bounds__(256) pool_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, PoolShape p)
@@ -449,6 +458,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const uint4* __restrict_
         }
         wo[w] = packed;
     }
+    POINTWISE_POST_RELU(wo);
     out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
 }
 
@@ -518,7 +528,8 @@ __global__ void __launch_bounds__(256) pointwise_fast_kernel(const uint4* __rest
                 if (lane0 + w * 4 + t < p.c) packed |= pointwise_exact_byte<U8>((wa[w] >> (8 * t)) & 0xff, (wb[w] >> (8 * t)) & 0xff, p) << (8 * t);
             wo[w] = packed;
         }
-        out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        POINTWISE_POST_RELU(wo);
+    out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
         return;
     }
     const uint64_t mg = f2_pack(TB200_MAGIC, TB200_MAGIC);
@@ -582,6 +593,7 @@ __global__ void __launch_bounds__(256) pointwise_fast_kernel(const uint4* __rest
                 wo[w] = packed;
             }
     }
+    POINTWISE_POST_RELU(wo);
     out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
 }
 
@@ -590,13 +602,19 @@ __global__ void __launch_bounds__(256) pointwise_fast_kernel(const uint4* __rest
 // (channel counts such as 255 / 384 need not be multiples of 4 at the seams).
 template <bool U8>
 __global__ void __launch_bounds__(256) concat_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                     long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+                                                     long long npix, int c, int c_write, int cp_in, int cp_out, int c_off, float s_in,
                                                      int z_in, float s_out, int z_out)
 {
+    // c_write >= c channels are written from c_off on: the last input of a concat also clears the output's pad lanes
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; // launchers guarantee totals < 2^31
-    if (idx >= (unsigned)(npix * c)) return;
-    const unsigned pix = idx / (unsigned)c;
-    const int ch = (int)(idx - pix * c);
+    if (idx >= (unsigned)(npix * c_write)) return;
+    const unsigned pix = idx / (unsigned)c_write;
+    const int ch = (int)(idx - pix * c_write);
+    if (ch >= c)
+    {
+        out[(size_t)pix * cp_out + c_off + ch] = 0;
+        return;
+    }
     const uint8_t v = in[(size_t)pix * cp_in + ch];
     int q;
     if (U8)
@@ -708,18 +726,21 @@ cudaError_t launch_conv_dw(const void* in, const void* w, void* out, const ConvS
         if (s.sh == 1)
         {
             constexpr int TW = 8;
-            const unsigned total = (unsigned)(s.n * s.oh * ((s.ow + TW - 1) / TW) * cw);
+            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            TB200_CHECK_32BIT(total * TW);
             conv_dw3x3_i8_kernel<TW, 1><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
         }
         else
         {
             constexpr int TW = 4;
-            const unsigned total = (unsigned)(s.n * s.oh * ((s.ow + TW - 1) / TW) * cw);
+            const long long total = (long long)s.n * s.oh * ((s.ow + TW - 1) / TW) * cw;
+            TB200_CHECK_32BIT(total * TW);
             conv_dw3x3_i8_kernel<TW, 2><<<blocks_for(total, 128), 128, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
         }
         return cudaGetLastError();
     }
-    const unsigned total = (unsigned)(s.n * s.oh * s.ow * (s.cp / 4));
+    const long long total = (long long)s.n * s.oh * s.ow * (s.cp / 4);
+    TB200_CHECK_32BIT(total * 4);
     if (e.is_uint8) conv_dw_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     else conv_dw_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (const uint8_t*)w, (uint8_t*)out, s, e);
     return cudaGetLastError();
@@ -779,12 +800,16 @@ cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, 
 {
     if (p.method == TB200_POOL_MAX && p.in_scale == p.out_scale && (!u8 || p.in_zero == p.out_zero) && !getenv("TB200_POOL_EXACT"))
     {
-        const unsigned tot = (unsigned)(p.n * p.oh * p.ow * (p.cp / 16));
+        const long long tot = (long long)p.n * p.oh * p.ow * (p.cp / 16);
+        TB200_CHECK_32BIT(tot * 16);
+        TB200_CHECK_32BIT((long long)p.n * p.h * p.w * (p.cp / 16));
         if (u8) pool_max_same_scale_kernel<true><<<blocks_for(tot, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, p);
         else pool_max_same_scale_kernel<false><<<blocks_for(tot, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, p);
         return cudaGetLastError();
     }
-    const unsigned total = (unsigned)(p.n * p.oh * p.ow * (p.cp / 4));
+    const long long total = (long long)p.n * p.oh * p.ow * (p.cp / 4);
+    TB200_CHECK_32BIT(total * 4);
+    TB200_CHECK_32BIT((long long)p.n * p.h * p.w * p.cp);
     if (u8) pool_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     else pool_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p);
     return cudaGetLastError();
@@ -857,19 +882,106 @@ cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long 
     return cudaGetLastError();
 }
 
-cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int cp_in, int cp_out, int c_off, float s_in,
+cudaError_t launch_concat_part(const void* in, void* out, long long npix, int c, int c_write, int cp_in, int cp_out, int c_off, float s_in,
                                int z_in, float s_out, int z_out, bool u8, cudaStream_t st)
 {
-    const long long total = npix * c;
+    const long long total = npix * c_write;
     TB200_CHECK_32BIT(total);
-    if (u8) concat_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
-    else concat_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
+    if (u8) concat_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, c_write, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
+    else concat_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, c_write, cp_in, cp_out, c_off, s_in, z_in, s_out, z_out);
+    return cudaGetLastError();
+}
+
+// ---- unary byte ops through a table (sigmoid_ref.c:84-172, hardswish_kernel_ref_uint8.c:41-80) ---------------------------
+// Thread = 16 bytes (the 16 channels of one channel block of one pixel).  The table lives in shared memory replicated per
+// bank group so that the 16 byte lookups of a thread rarely conflict; pad lanes (channel >= c) are written as 0.
+__global__ void __launch_bounds__(256) byte_lut_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const uint8_t* __restrict__ lut,
+                                                       long long nvec, int c, int cvec)
+{
+    __shared__ uint8_t tab[256];
+    tab[threadIdx.x] = __ldg(lut + threadIdx.x);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 v = __ldg(in + i);
+    const int c0 = (int)(i % cvec) * 16;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        uint32_t r = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+        {
+            const uint32_t b = (w[j] >> (8 * t)) & 0xffu;
+            const uint32_t y = (c0 + j * 4 + t < c) ? (uint32_t)tab[b] : 0u;
+            r |= y << (8 * t);
+        }
+        o[j] = r;
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+cudaError_t launch_byte_lut(const void* in, void* out, const uint8_t* lut, long long bytes, int c, int cp, cudaStream_t st)
+{
+    const long long nvec = bytes / 16;
+    byte_lut_kernel<<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, lut, nvec, c, cp / 16);
+    return cudaGetLastError();
+}
+
+// ---- softmax over channels (softmax_kernel_ref_int8.c:41-118, softmax_kernel_ref_uint8.c:41-120; helpers
+//      softmax_kernel_ref.h:36-82) ---------------------------------------------------------------------------------------------
+// The reference dequantises, takes the per-position maximum, exp() in DOUBLE stored to float, a float running sum in channel
+// order, a float division and round(f / s_out).  One thread per (image, position) walks the channels in the same order so the
+// float sum has the same rounding sequence; CUDA's double exp() differs from glibc's by < 1 ulp of double, i.e. the float it
+// rounds to is the same except on a double-rounding tie.
+template <bool U8>
+__global__ void __launch_bounds__(128) softmax_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long npix, int c, int cp,
+                                                      float s_in, int z_in, float s_out, int z_out)
+{
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const uint8_t* ip = in + (size_t)pix * cp;
+    uint8_t* op = out + (size_t)pix * cp;
+    auto deq = [&](int k) -> float
+    {
+        const uint8_t b = ip[k];
+        return U8 ? __fmul_rn((float)b - (float)z_in, s_in) : __fmul_rn((float)(int)(int8_t)b, s_in);
+    };
+    float mx = deq(0);
+    for (int k = 1; k < c; k++)
+    {
+        const float v = deq(k);
+        if (mx < v) mx = v;
+    }
+    float sum = 0.f;
+    for (int k = 0; k < c; k++) sum = __fadd_rn(sum, (float)exp((double)__fsub_rn(deq(k), mx)));
+    for (int k = 0; k < c; k++)
+    {
+        const float e = (float)exp((double)__fsub_rn(deq(k), mx));
+        const float f = __fdiv_rn(e, sum);
+        int q = (int)roundf(__fdiv_rn(f, s_out));
+        if (U8) q = clamp_u8(q + z_out);
+        else q = clamp_i8(q);
+        op[k] = (uint8_t)q;
+    }
+    for (int k = c; k < cp; k++) op[k] = 0;
+}
+
+cudaError_t launch_softmax(const void* in, void* out, long long npix, int c, int cp, float s_in, int z_in, float s_out, int z_out, bool u8,
+                           cudaStream_t st)
+{
+    TB200_CHECK_32BIT(npix);
+    if (u8) softmax_kernel<true><<<blocks_for(npix, 128), 128, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp, s_in, z_in, s_out, z_out);
+    else softmax_kernel<false><<<blocks_for(npix, 128), 128, 0, st>>>((const uint8_t*)in, (uint8_t*)out, npix, c, cp, s_in, z_in, s_out, z_out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st)
 {
-    const unsigned total = (unsigned)(n * h * scale * w * scale * (cp / 16));
+    const long long total = (long long)n * h * scale * w * scale * (cp / 16);
+    TB200_CHECK_32BIT(total * 16);
     upsample_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, n, h, w, cp / 16, scale);
     return cudaGetLastError();
 }

@@ -83,6 +83,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds_f2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr)
 {
     uint4 v;

@@ -33,6 +33,7 @@ extern "C" {
 #include "operator/prototype/eltwise_param.h"
 #include "operator/prototype/concat_param.h"
 #include "operator/prototype/upsample_param.h"
+#include "operator/prototype/softmax_param.h"
 }
 
 #include <cstdlib>
@@ -46,7 +47,8 @@ extern "C" {
 
 namespace {
 
-const int kSupportedOps[] = {OP_CONST, OP_INPUT, OP_CONV, OP_FC, OP_POOL, OP_RELU, OP_ELTWISE, OP_CONCAT, OP_UPSAMPLE, OP_DROPOUT};
+const int kSupportedOps[] = {OP_CONST,  OP_INPUT,    OP_CONV,    OP_FC,      OP_POOL,    OP_RELU,      OP_ELTWISE, OP_CONCAT,
+                             OP_UPSAMPLE, OP_DROPOUT, OP_SOFTMAX, OP_SIGMOID, OP_FLATTEN, OP_RESHAPE, OP_HARDSWISH};
 
 struct B200Graph
 {
@@ -61,6 +63,8 @@ struct B200Device
 };
 
 tb200_context* g_ctx = nullptr;
+std::vector<int> g_ctx_devs; // the CUDA ordinals g_ctx was created over
+int g_live_graphs = 0;       // device graphs alive on g_ctx
 
 int b200_dev_init(struct device* dev)
 {
@@ -68,17 +72,110 @@ int b200_dev_init(struct device* dev)
     return 0; // the GPU is bound lazily at the first pre_run so that init_tengine() works on GPU-less hosts
 }
 
-int ensure_context()
+// The GPUs behind the device: the option blob of set_context_device(ctx, "B200", &opt, sizeof opt) (tb200_device_option, the
+// analogue of trt_option, source/device/tensorrt/trt_define.h:36-42) or, for applications that pass none (tm_benchmark,
+// tm_classification_*), the environment: TG_B200_GPUS=<count> (or "all"), TG_B200_GPU=<first ordinal>.  One process, one
+// application thread; the batch of every run is sharded over the group inside libtengine_b200.so.
+int ensure_context(const void* options)
 {
-    if (g_ctx) return 0;
-    int gpu = 0;
-    if (const char* e = getenv("TG_B200_GPU")) gpu = atoi(e);
-    if (tb200_context_create(gpu, &g_ctx) != 0)
+    int first = 0, count = 1;
+    if (const char* e = getenv("TG_B200_GPU")) first = atoi(e);
+    if (const char* e = getenv("TG_B200_GPUS")) count = (0 == strcmp(e, "all")) ? tb200_device_count() : atoi(e);
+    if (options)
+    {
+        const tb200_device_option* o = (const tb200_device_option*)options;
+        if (o->dev_name && 0 == strcmp(o->dev_name, B200_DEV_NAME))
+        {
+            if (o->num_gpus > 0) count = o->num_gpus;
+            if (o->first_gpu > 0) first = o->first_gpu;
+        }
+    }
+    if (count < 1) count = 1;
+    std::vector<int> devs;
+    for (int i = 0; i < count; i++) devs.push_back(first + i);
+    if (const char* e = getenv("TG_B200_GPU_LIST")) // explicit ordinals, e.g. "0,2,4,6"; a repeated ordinal = several shards on one GPU (tests)
+    {
+        devs.clear();
+        for (const char* p = e; *p;)
+        {
+            char* end;
+            const long v = strtol(p, &end, 10);
+            if (end == p) break;
+            devs.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (devs.empty()) devs.push_back(first);
+        count = (int)devs.size(), first = devs[0];
+    }
+    if (g_ctx && devs == g_ctx_devs) return 0;
+    if (g_ctx)
+    {
+        // another graph asks for a different group (e.g. a second context with another option blob)
+        if (g_live_graphs > 0)
+        {
+            TLOG_ERR("Tengine: B200 device: a graph is still prepared on another GPU group; postrun it first\n");
+            return -1;
+        }
+        tb200_context_destroy(g_ctx);
+        g_ctx = nullptr;
+    }
+    g_ctx_devs = devs;
+    const int rc = count == 1 ? tb200_context_create(first, &g_ctx) : tb200_context_create_multi(devs.data(), count, &g_ctx);
+    if (rc != 0)
     {
         TLOG_ERR("Tengine: B200 device: %s\n", tb200_last_error());
         return -1;
     }
     return 0;
+}
+
+// ---- what the engine can take, node by node (the planner's own predicates, tengine_b200/csrc/engine.cu).  An op type with a
+//      node that fails its predicate is left to the CPU device for this graph (the splitter works on op types, split.c:140). ----
+bool node_supported(struct graph* ir_graph, struct node* node)
+{
+    struct tensor* in0 = node->input_num ? get_ir_graph_tensor(ir_graph, node->input_tensors[0]) : nullptr;
+    struct tensor* out0 = node->output_num ? get_ir_graph_tensor(ir_graph, node->output_tensors[0]) : nullptr;
+    switch (node->op.type)
+    {
+    case OP_CONV:
+    {
+        const struct conv_param* p = (const struct conv_param*)node->op.param_mem;
+        if (!in0 || in0->dim_num != 4) return false;
+        const int cg = in0->dims[1] / (p->group > 0 ? p->group : 1), og = out0->dims[1] / (p->group > 0 ? p->group : 1);
+        const bool depthwise = p->group > 1 && cg == 1 && og == 1;
+        if (p->group > 1 && !depthwise && ((cg % 4) || (og % 4))) return false;
+        return true;
+    }
+    case OP_FC:
+    {
+        struct tensor* w = get_ir_graph_tensor(ir_graph, node->input_tensors[1]);
+        return w->dim_num == 2 && out0 && w->dims[0] == out0->dims[1]; // the [K, N] layout (fc_ref.c need_trans) stays on the CPU
+    }
+    case OP_POOL: return in0 && in0->dim_num == 4;
+    case OP_ELTWISE:
+    {
+        const int t = ((const struct eltwise_param*)node->op.param_mem)->type;
+        if (node->input_num != 2 || (t != ELT_SUM && t != ELT_PROD)) return false;
+        struct tensor* in1 = get_ir_graph_tensor(ir_graph, node->input_tensors[1]);
+        return in1->tensor_type != TENSOR_TYPE_CONST && in1->elem_num == in0->elem_num;
+    }
+    case OP_CONCAT: return in0 && in0->dim_num == 4 && node->input_num <= 4 && ((const struct concat_param*)node->op.param_mem)->axis == 1;
+    case OP_UPSAMPLE:
+    {
+        const float sc = ((const struct upsample_param*)node->op.param_mem)->scale;
+        return in0 && in0->dim_num == 4 && sc == (float)(int)sc && sc >= 1.f;
+    }
+    case OP_SOFTMAX:
+    {
+        int axis = ((const struct softmax_param*)node->op.param_mem)->axis;
+        if (in0 && axis < 0) axis += in0->dim_num;
+        return axis == 1;
+    }
+    case OP_HARDSWISH: return in0 && in0->data_type == TENGINE_DT_UINT8; // the reference has no int8 kernel (hardswish_ref.c:59-66)
+    case OP_FLATTEN:
+    case OP_RESHAPE: return in0 && out0 && in0->dims[0] == out0->dims[0] && in0->dim_num <= 4 && out0->dim_num <= 4;
+    default: return true;
+    }
 }
 
 void fill_tensor_desc(const struct tensor* t, tb200_tensor_desc* d)
@@ -105,8 +202,7 @@ int conv_recipe(const struct conv_param* p, const struct tensor* in, const struc
 int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options)
 {
     (void)dev;
-    (void)options; // NULL for apps that never call set_context_device (scheduler.c:49-57)
-    if (ensure_context() != 0) return -1;
+    if (ensure_context(options) != 0) return -1; // options: NULL for apps that never call set_context_device (scheduler.c:49-57)
     struct graph* ir_graph = subgraph->graph;
 
     std::map<uint16_t, int> tmap; // ir tensor id -> index in the ABI tensor table
@@ -174,11 +270,6 @@ int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options
             else
             {
                 L.op = TB200_OP_FC;
-                if (w->dims[0] != oc)
-                {
-                    TLOG_ERR("Tengine: B200 device: FC weight layout [K,N] (need_trans) is not supported\n");
-                    return -1;
-                }
             }
             break;
         }
@@ -222,6 +313,15 @@ int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options
             L.up_scale = (int)((const struct upsample_param*)node->op.param_mem)->scale;
             break;
         case OP_DROPOUT: L.op = TB200_OP_IDENTITY; break;
+        case OP_SOFTMAX:
+            L.op = TB200_OP_SOFTMAX;
+            L.axis = ((const struct softmax_param*)node->op.param_mem)->axis;
+            if (L.axis < 0) L.axis += in0->dim_num;
+            break;
+        case OP_SIGMOID: L.op = TB200_OP_SIGMOID; break;
+        case OP_HARDSWISH: L.op = TB200_OP_HARDSWISH; break;
+        case OP_FLATTEN:
+        case OP_RESHAPE: L.op = TB200_OP_RESHAPE; break; // the output tensor's dims carry the new shape
         default: TLOG_ERR("Tengine: B200 device: op %d reached pre_run but is not supported\n", op); return -1;
         }
         layers.push_back(L);
@@ -252,6 +352,7 @@ int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options
         return -1;
     }
     subgraph->device_graph = bg;
+    g_live_graphs++;
     return 0;
 }
 
@@ -299,6 +400,7 @@ int b200_dev_postrun(struct device* dev, struct subgraph* subgraph)
     if (bg)
     {
         tb200_graph_postrun(bg->graph);
+        g_live_graphs--;
         delete bg;
         subgraph->device_graph = nullptr;
     }
@@ -353,10 +455,27 @@ int b200_split_graph(struct graph* ir_graph)
     // reached either because the context names this device, or through the TG_DEFAULT_DEVICE seam on the CPU device;
     // the splitter assigns context->device to accelerator subgraphs without a NULL check (split.c:214-215)
     ir_graph->attribute->context->device = &g_b200.base;
+    struct vector* allowed_all = create_vector(sizeof(int), nullptr);
+    struct vector* blocked_all = create_vector(sizeof(int), nullptr);
+    struct vector* precision = create_vector(sizeof(int), nullptr);
+    b200_describe(&g_b200.base, allowed_all, blocked_all, precision);
+    // op types with a node the engine cannot take go to the CPU device for this graph (instead of failing pre_run)
+    std::vector<char> veto(OP_BUILTIN_LAST, 0);
+    for (int i = 0; i < ir_graph->node_num; i++)
+    {
+        struct node* node = get_ir_graph_node(ir_graph, i);
+        if (node->op.type < OP_BUILTIN_LAST && !node_supported(ir_graph, node)) veto[node->op.type] = 1;
+    }
     struct vector* allowed_ops = create_vector(sizeof(int), nullptr);
     struct vector* blocked_ops = create_vector(sizeof(int), nullptr);
-    struct vector* precision = create_vector(sizeof(int), nullptr);
-    b200_describe(&g_b200.base, allowed_ops, blocked_ops, precision);
+    for (int i = 0; i < OP_BUILTIN_LAST; i++)
+    {
+        bool ok = false;
+        for (int op : kSupportedOps) ok |= (op == i);
+        push_vector_data((ok && !veto[i]) ? allowed_ops : blocked_ops, &i);
+    }
+    release_vector(allowed_all);
+    release_vector(blocked_all);
     split_graph_node_to_sub_graph(ir_graph, allowed_ops, blocked_ops, precision);
     release_vector(allowed_ops);
     release_vector(blocked_ops);

@@ -151,6 +151,21 @@ class GraphDef:
         out = self.add_tensor(src["dims"], src["scale"], src["zero_point"])
         return self._layer(abi.OP_IDENTITY, [x], out)
 
+    def softmax(self, x, out_scale, out_zero=0, axis=1):
+        return self._layer(abi.OP_SOFTMAX, [x], self.add_tensor(self.dims(x), out_scale, out_zero), axis=int(axis))
+
+    def sigmoid(self, x, out_scale, out_zero=0):
+        return self._layer(abi.OP_SIGMOID, [x], self.add_tensor(self.dims(x), out_scale, out_zero))
+
+    def hardswish(self, x, out_scale, out_zero=0):
+        return self._layer(abi.OP_HARDSWISH, [x], self.add_tensor(self.dims(x), out_scale, out_zero))
+
+    def flatten(self, x):
+        """OP_FLATTEN (axis 1..3) / OP_RESHAPE to [N, C*H*W, 1, 1]: the same bytes in NCHW order, same quantisation."""
+        n, c, h, w = self.dims(x)
+        src = self.tensors[x]
+        return self._layer(abi.OP_RESHAPE, [x], self.add_tensor((n, c * h * w, 1, 1), src["scale"], src["zero_point"]))
+
     # ---- C tables ------------------------------------------------------------------------------
     def c_tables(self):
         """(TensorDesc[], LayerDesc[]) ctypes arrays; numpy constants stay referenced by self."""

@@ -61,6 +61,17 @@ def lib():
         L.tb200_graph_num_launches.argtypes = [C.c_void_p]
         L.tb200_context_destroy.argtypes = [C.c_void_p]
         L.tb200_context_stream.argtypes = [C.c_void_p]
+        L.tb200_context_create_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.tb200_context_num_gpus.argtypes = [C.c_void_p]
+        L.tb200_context_gpu.argtypes = [C.c_void_p, C.c_int]
+        L.tb200_context_stream_of.argtypes = [C.c_void_p, C.c_int]
+        L.tb200_context_stream_of.restype = C.c_void_p
+        L.tb200_context_broadcast_kind.argtypes = [C.c_void_p]
+        L.tb200_context_broadcast_kind.restype = C.c_char_p
+        L.tb200_graph_num_shards.argtypes = [C.c_void_p]
+        L.tb200_graph_shard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb200_graph_arena_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb200_graph_broadcast_weights.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -75,16 +86,34 @@ def device_count():
 
 
 class Context:
-    """interface->init / release_device: binds one GPU."""
+    """interface->init / release_device: binds one GPU, or (devices=[...]) a group of GPUs driven by this process over
+    which every graph shards its batch (tb200_context_create_multi)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.h = C.c_void_p()
-        _check(lib().tb200_context_create(int(device), C.byref(self.h)))
-        self.device = device
+        if devices is None:
+            _check(lib().tb200_context_create(int(device), C.byref(self.h)))
+            self.devices = [int(device)]
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(lib().tb200_context_create_multi(arr, len(devices), C.byref(self.h)))
+            self.devices = [int(d) for d in devices]
+        self.device = self.devices[0]
 
     @property
     def stream(self):
         return lib().tb200_context_stream(self.h)
+
+    @property
+    def num_gpus(self):
+        return lib().tb200_context_num_gpus(self.h)
+
+    def stream_of(self, index):
+        return lib().tb200_context_stream_of(self.h, int(index))
+
+    @property
+    def broadcast_kind(self):
+        return lib().tb200_context_broadcast_kind(self.h).decode()
 
     def close(self):
         if self.h:
@@ -169,6 +198,21 @@ class Graph:
         p, n = C.c_void_p(), C.c_size_t()
         _check(lib().tb200_graph_weight_arena(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def shards(self):
+        """[(cuda device, first image, number of images)] -- how the batch was cut over the context's GPUs."""
+        out = []
+        for i in range(lib().tb200_graph_num_shards(self.h)):
+            d, f, n = C.c_int(), C.c_int(), C.c_int()
+            _check(lib().tb200_graph_shard(self.h, i, C.byref(d), C.byref(f), C.byref(n)))
+            out.append((d.value, f.value, n.value))
+        return out
+
+    def arena_bytes(self):
+        """(activation arena, the same without slot reuse, weight arena) in bytes, GPU 0's shard."""
+        a, u, w = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _check(lib().tb200_graph_arena_bytes(self.h, C.byref(a), C.byref(u), C.byref(w)))
+        return a.value, u.value, w.value
 
     def close(self):
         if self.h:

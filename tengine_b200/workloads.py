@@ -170,6 +170,30 @@ class QuantBuilder:
     def identity(self, x):
         return _H(self.g.identity(x.tid), x.act)
 
+    def flatten(self, x):
+        return _H(self.g.flatten(x.tid), x.act.reshape(x.act.shape[0], -1, 1, 1))
+
+    def softmax(self, x):
+        a = self.torch.softmax(x.act, dim=1)
+        # probabilities: the reference's models quantise them over [0, 1]
+        so, zo = (np.float32(1.0 / 255.0), 0) if self.u8 else (np.float32(1.0 / 127.0), 0)
+        return _H(self.g.softmax(x.tid, so, zo), a)
+
+    def sigmoid(self, x):
+        a = self.torch.sigmoid(x.act)
+        so, zo = (np.float32(1.0 / 255.0), 0) if self.u8 else (np.float32(1.0 / 127.0), 0)
+        return _H(self.g.sigmoid(x.tid, so, zo), a)
+
+    def hardswish(self, x):
+        a = self.torch.nn.functional.hardswish(x.act)
+        so, zo = self._act_q(a)
+        return _H(self.g.hardswish(x.tid, so, zo), a)
+
+    def mul(self, x, y):
+        a = x.act * y.act
+        so, zo = self._act_q(a)
+        return _H(self.g.eltwise(x.tid, y.tid, so, zo, abi.ELT_PROD), a)
+
     def finish(self, outs):
         for o in outs:
             self.g.mark_output(o.tid)
@@ -212,6 +236,20 @@ def mobilenet_v1(data_type=abi.DT_INT8, batch=1, res=224, seed=1234, width=1.0, 
     return b.finish([x]), b
 
 
+def tail_net(data_type=abi.DT_INT8, batch=2, seed=11):
+    """The glue ops around the classifier / detection heads: sigmoid * x (SiLU as the reference's int8 graphs spell it),
+    hardswish (uint8 only, like the reference), flatten of a C x H x W tensor, FC, softmax."""
+    b = QuantBuilder(data_type, batch, 3, 12, 12, seed)
+    x = b.conv(b.input, 24, 3, stride=1, pad=1, activation=-1)
+    x = b.mul(x, b.sigmoid(x))
+    if b.u8:
+        x = b.hardswish(b.conv(x, 20, 1, activation=-1))
+    x = b.pool(x, abi.POOL_MAX, 2, 2)
+    f = b.flatten(x)
+    y = b.softmax(b.fc(f, 10))
+    return b.finish([y, x]), b
+
+
 def tiny_net(data_type=abi.DT_INT8, batch=2, seed=7):
     """A few layers of every kind for fast CPU-oracle parity tests."""
     b = QuantBuilder(data_type, batch, 3, 20, 20, seed)
@@ -231,7 +269,7 @@ def tiny_net(data_type=abi.DT_INT8, batch=2, seed=7):
     return b.finish([f, l]), b
 
 
-def resnet50(data_type=abi.DT_UINT8, batch=1, res=224, seed=1234, width=1.0, classes=1000, blocks=(3, 4, 6, 3)):
+def resnet50(data_type=abi.DT_UINT8, batch=1, res=224, seed=1234, width=1.0, classes=1000, blocks=(3, 4, 6, 3), softmax=False):
     """ResNet-50 as in benchmark/models/resnet50_benchmark.tmfile (Caffe layout): 7x7 s2 stem with fused ReLU, 3x3 s2
     max-pool (caffe_flavor 1 -> real pads 0,1,0,1), bottlenecks whose projection / first 1x1 carry the stride, Eltwise-sum
     followed by a STANDALONE ReLU node (each re-quantises), global average pool, FC 2048->1000 (Softmax stays on the CPU)."""
@@ -254,6 +292,8 @@ def resnet50(data_type=abi.DT_UINT8, batch=1, res=224, seed=1234, width=1.0, cla
             x = b.relu(x)
     x = b.pool(x, abi.POOL_AVG, b.g.dims(x.tid)[2], 1, global_pool=True, caffe_flavor=1)
     x = b.fc(x, classes)
+    if softmax:  # the tail of the reference's resnet50 tmfile (fc1000 -> prob)
+        x = b.softmax(x)
     return b.finish([x]), b
 
 

@@ -149,6 +149,12 @@ CONV_CASES = [
     (1, 24, 10, 10, 40, 5, 1, 2, 1),    # 5x5
     (1, 20, 9, 9, 255, 1, 1, 0, 1),     # odd Cout (YOLO head), Cin not multiple of 16
     (2, 16, 12, 12, 16, 3, 1, 2, 1),    # pad > (k-1)/2
+    (2, 3, 64, 48, 64, 7, 2, 3, 1),     # 7x7 stem, TMA-staged window (W % 16 == 0)
+    (3, 3, 40, 32, 16, 3, 1, 1, 1),     # 3x3 s1 stem, several tiles per image, ragged tile rows
+    (2, 3, 37, 48, 24, 3, 2, 0, 1),     # stem without padding
+    (2, 32, 21, 19, 64, 3, 1, 1, 1),    # 32-channel 3x3 (window kernel, NHWC 32 B/pixel), ragged tiles
+    (2, 24, 18, 18, 40, 3, 2, 1, 1),    # 24 real channels in a 32-byte pixel: pad lanes must stay out of the uint8 sums
+    (1, 12, 20, 20, 16, 3, 1, 1, 1),    # 12 real channels in a 16-byte pixel
 ]
 
 

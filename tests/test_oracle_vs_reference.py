@@ -159,3 +159,41 @@ def test_benchmark_graphs_with_inplace_scales(oracle, reference, net, dtype):
         got = oracle.run(h, [want[t] for t in src])
         d = np.abs(got[h.outputs[0]].astype(np.int32) - want[L["output"]].astype(np.int32))
         assert d.max() <= 1, f"{net} layer {li} {abi.OP_NAMES[L['op']]}: {int(d.max())} LSB"
+
+
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+def test_tail_ops_sigmoid_mul_hardswish_flatten_softmax(oracle, reference, dtype):
+    """Glue ops around the classifier / detection heads: Sigmoid, Eltwise-PROD (x * sigmoid(x): the int8
+    spelling of YOLOv5s' activation), HardSwish (uint8 only in the reference), Flatten, FC, Softmax -- oracle == reference."""
+    g, b = workloads.tail_net(dtype, batch=2)
+    x = b.random_input(3)
+    want, _ = reference.run(g, [x], want=layer_outputs(g))
+    got = oracle.run(g, [x])
+    kinds = set()
+    for li, L in enumerate(g.layers):
+        t = L["output"]
+        kinds.add(abi.OP_NAMES[L["op"]])
+        assert np.array_equal(got[t], want[t]), (li, abi.OP_NAMES[L["op"]])
+        assert len(np.unique(want[t])) > 8, "test vacuous"
+    assert {"sigmoid", "softmax", "reshape", "eltwise"} <= kinds and (("hardswish" in kinds) == (dtype == abi.DT_UINT8))
+
+
+def test_uint8_fc_uses_the_bias_tensors_own_scale(oracle, reference):
+    """fc_ref.c:141-146 multiplies the int32 bias by bias_tensor->scale, which a tmfile may set to something other than
+    fl(s_in*s_w) (e.g. computed in double by the quantisation tool)."""
+    rng = np.random.default_rng(3)
+    g = GraphDef(abi.DT_UINT8)
+    x = g.input(3, 64, 2, 2, 0.02, 128)
+    w = rng.integers(0, 256, (40, 256)).astype(np.uint8)
+    bias = rng.integers(-30000, 30000, 40).astype(np.int32)
+    y = g.fc(x, w, bias, [0.004], 0.05, 120, weight_zero=119)
+    g.layers[-1]["bias_scale"] = float(np.float32(0.02 * 0.004 * 1.37))
+    g.mark_output(y)
+    xin = rng.integers(0, 256, (3, 64, 2, 2)).astype(np.uint8)
+    want, _ = reference.run(g, [xin])
+    got = oracle.run(g, [xin], uint8_mode=0)[y]
+    d = np.abs(got.astype(int) - want[y].astype(int))
+    assert d.max() <= 1 and len(np.unique(want[y])) > 20
+    g.layers[-1]["bias_scale"] = float(np.float32(0.02) * np.float32(0.004))
+    other = oracle.run(g, [xin], uint8_mode=0)[y]
+    assert np.abs(other.astype(int) - want[y].astype(int)).max() > 1, "test vacuous: the bias scale does not matter here"

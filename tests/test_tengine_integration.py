@@ -94,3 +94,86 @@ def test_unmodified_tm_benchmark_on_b200():
                        text=True, timeout=600)
     txt = r.stdout + r.stderr
     assert r.returncode == 0 and "min =" in txt, txt[-800:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["mobilenet_v1_uint8", "resnet50_uint8"])
+def test_unmodified_tm_classification_uint8_on_b200(model):
+    """examples/tm_classification_uint8.c, compiled unmodified (create_graph(NULL, ...), TENGINE_MODE_UINT8): the
+    TG_DEFAULT_DEVICE=B200 seam routes the uint8 graph -- for ResNet-50 including max-pool, eltwise, ReLU, Flatten-less FC
+    and Softmax -- to the device.  The CPU path is an fp32 simulation (+-1 LSB per layer), so scores are compared with a
+    tolerance of a few output LSBs instead of as strings."""
+    exe = os.path.join(BUILD, "tm_classification_uint8")
+    path = os.path.join(MODELS, model + ".tmfile")
+    img = os.path.join(MODELS, "test.bmp")
+    if not (os.path.exists(exe) and os.path.exists(path) and os.path.exists(img)):
+        pytest.skip("integration build / model files absent (python oracle/make_models.py)")
+    res = {}
+    for dev in ("CPU", "B200"):
+        env = dict(os.environ)
+        env.pop("TG_DEFAULT_DEVICE", None)
+        if dev == "B200":
+            env["TG_DEFAULT_DEVICE"] = "B200"
+        r = subprocess.run([exe, "-m", path, "-i", img, "-g", "224,224", "-r", "2", "-t", "8"], capture_output=True, text=True, env=env, timeout=600)
+        txt = r.stdout + r.stderr
+        assert r.returncode == 0, txt[-800:]
+        rows = [l.split(",") for l in txt.splitlines() if l.count(",") == 1 and l.strip().replace(".", "").replace(",", "").replace(" ", "").replace("-", "").isdigit()]
+        assert len(rows) == 5, txt[-800:]
+        res[dev] = [(float(a), int(b)) for a, b in rows]
+    top_cpu, top_dev = res["CPU"][0][0], res["B200"][0][0]
+    assert abs(top_cpu - top_dev) <= 0.05 * max(abs(top_cpu), 1e-3) + 0.05, (res["CPU"], res["B200"])
+
+
+def _tmfile_case(name):
+    from tengine_b200 import abi, workloads
+
+    if name == "yolov3_tiny_uint8":
+        g, b = workloads.yolov3_tiny(abi.DT_UINT8, batch=4)
+        return g, b, list(g.outputs)
+    g, b = workloads.resnet50(abi.DT_UINT8, batch=4, softmax=True)
+    return g, b, [g.outputs[0], g.layers[-1]["inputs"][0]]  # prob, fc1000 (oracle/make_models.py)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["yolov3_tiny_uint8", "resnet50_uint8"])
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_full_size_tmfile_through_run_graph_on_b200(oracle, name, gpus):
+    """C3 / C4 model files (written by the reference's own tmfile writer) loaded by the reference's serializer and executed by
+    run_graph() on device "B200" -- one GPU, and a two-GPU group selected through the set_context_device option blob
+    (tb200_device_option; on a one-GPU box TG_B200_GPU_LIST=0,0 makes the group two shards on the same GPU).  Batch 4.
+    The bytes must equal the exact-integer oracle's (the CPU device itself is only within a few LSB of that)."""
+    from oracle.pyoracle import Reference, run_tmfile
+    from tengine_b200 import runtime as rt
+
+    path = os.path.join(MODELS, name + ".tmfile")
+    if not (_have_integration() and os.path.exists(path)):
+        pytest.skip("integration build / model files absent")
+    g, b, outs = _tmfile_case(name)
+    x = b.random_input(21)
+    ref = Reference(libdir=BUILD)
+    env = {"TG_B200_GPU_LIST": "0,0"} if (gpus == 2 and rt.device_count() < 2) else {}
+    got, ms = run_tmfile(ref, path, x, [g.dims(t) for t in outs], device="B200", num_gpus=gpus if gpus > 1 else 0, env=env, warmup=1, loops=2)
+    want = oracle.run(g, [x], uint8_mode=0)
+    for o, t in zip(got, outs):
+        assert np.array_equal(o, want[t]), (name, t, int(np.abs(o.astype(int) - want[t].astype(int)).max()))
+    assert len(np.unique(got[-1])) > 30
+
+
+@pytest.mark.gpu
+def test_unmodified_tm_benchmark_two_gpu_group():
+    """tm_benchmark -d B200 unmodified, the GPU group chosen by the environment (TG_B200_GPUS / TG_B200_GPU_LIST)."""
+    from tengine_b200 import runtime as rt
+
+    exe = os.path.join(BUILD, "tm_benchmark")
+    model = os.path.join(MODELS, "mobilenet_v1_int8.tmfile")
+    if not (os.path.exists(exe) and os.path.exists(model)):
+        pytest.skip("integration build / model files absent")
+    env = dict(os.environ)
+    if rt.device_count() >= 2:
+        env["TG_B200_GPUS"] = "2"
+    else:
+        env["TG_B200_GPU_LIST"] = "0,0"
+    r = subprocess.run([exe, "-d", "B200", "-m", model, "-i", "16,3,224,224", "-f", "2", "-r", "5", "-t", "8"], capture_output=True, text=True,
+                       timeout=600, env=env)
+    txt = r.stdout + r.stderr
+    assert r.returncode == 0 and "min =" in txt, txt[-800:]
