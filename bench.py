@@ -39,6 +39,8 @@ WORKLOADS = {
     "resnet50_int8": ("resnet50", "int8", 224, 512, "images/sec int8 CNN inference (ResNet-50 224x224)"),
     "yolov3_tiny_uint8": ("yolov3_tiny", "uint8", 416, 16, "images/sec uint8 CNN inference (YOLOv3-tiny 416x416)"),
     "yolov3_tiny_int8": ("yolov3_tiny", "int8", 416, 16, "images/sec int8 CNN inference (YOLOv3-tiny 416x416)"),
+    "yolov5s_int8": ("yolov5s", "int8", 640, 8, "images/sec int8 CNN inference (YOLOv5s 640x640)"),
+    "yolov5s_uint8": ("yolov5s", "uint8", 640, 8, "images/sec uint8 CNN inference (YOLOv5s 640x640)"),
 }
 
 

@@ -211,6 +211,15 @@ TB200_API int tb200_graph_postrun(tb200_graph* g);
  * batch is sharded over several GPUs; identical layout on every rank for identical graphs. */
 TB200_API int tb200_graph_weight_arena(tb200_graph* g, void** device_ptr, size_t* bytes);
 
+/* Packed-weight cache (the CPU analogue is conv_hcl_prerun's interleaved weights, conv_kernel_x86.c:2137-2209,
+ * rebuilt at every prerun): with a directory set -- here or with TG_B200_PACK_CACHE -- prerun stores the packed arena image under a
+ * hash of everything it depends on (descriptors, kernel choices, weights, biases, scales) and later preruns of the same model read
+ * it back instead of packing.  NULL or "" disables.  tb200_graph_pack_cache_state: 0 no cache, 1 packed + written, 2 read.
+ * (The north star's int4 weights are not offered: Tengine has no int4 tensor type, c_api.h:58-63, so nothing could be checked
+ * against the reference; int8 / uint8 weights are what its files carry.) */
+TB200_API int tb200_pack_cache_dir(const char* dir);
+TB200_API int tb200_graph_pack_cache_state(tb200_graph* g);
+
 /* multi-GPU contexts: re-send the arena (after a caller filled GPU 0's arena itself, TB200_PRERUN_NO_WEIGHTS) */
 TB200_API int tb200_graph_broadcast_weights(tb200_graph* g);
 /* how the batch was cut: shard `index` runs images [first_image, first_image + num_images) on CUDA device *cuda_device */
@@ -229,6 +238,34 @@ TB200_API int tb200_graph_read_tensor(tb200_graph* g, int tensor_id, void* host_
 TB200_API int tb200_graph_profile(tb200_graph* g, float* layer_ms, int num_layers);
 /* algorithmic work of one launch: 2*MACs of conv+fc, and bytes = conv/fc in+out activations + weights + bias */
 TB200_API int tb200_graph_work(tb200_graph* g, double* ops, double* bytes);
+
+/* ---- detection post-processing on the device ------------------------------------------------------
+ * YOLO region decode + score threshold + sort + NMS on the graph's quantised output tensors where they lie in HBM (after
+ * tb200_graph_run / tb200_graph_launch); only the kept boxes come back.  Restates the application code of
+ * examples/tm_yolov3_tiny_uint8.cpp:57-132,176-250,464-500 (the head tensors are [N, anchors*(5+classes), H, W]; proposals are
+ * generated head by head in the order given here, sorted by the example's quicksort, suppressed greedily). */
+typedef struct tb200_yolo_head
+{
+    int32_t output_index; /* which graph output */
+    int32_t stride;       /* 32, 16, 8 */
+    float anchors[6];     /* (w, h) of the three anchors of this head */
+} tb200_yolo_head;
+typedef struct tb200_yolo_params
+{
+    int32_t num_heads;    /* <= 3 */
+    tb200_yolo_head heads[3];
+    int32_t num_classes;  /* 80 */
+    float prob_threshold, nms_threshold;
+    int32_t max_candidates; /* per image, before NMS (0: 4096) */
+} tb200_yolo_params;
+typedef struct tb200_detection
+{
+    float x, y, w, h; /* box in network-input pixels (cv::Rect_<float> of the example) */
+    float prob;
+    int32_t label;
+} tb200_detection;
+/* out: [images][max_per_image]; counts[image] = boxes kept (negative: more than fit -- -needed is returned there) */
+TB200_API int tb200_graph_yolo_detect(tb200_graph* g, const tb200_yolo_params* p, tb200_detection* out, int max_per_image, int32_t* counts);
 
 /* ---- kernel launchers (device pointers; NHWC with channels padded to tb200k_cpad(c)) --------------- */
 typedef struct tb200k_epilogue
@@ -272,6 +309,17 @@ TB200_API int tb200k_gemm_i8(const void* in, const void* weight, void* out, int6
 /* layout conversion host-NCHW <-> device-NHWC(pad) */
 TB200_API int tb200k_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, void* stream);
 TB200_API int tb200k_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, void* stream);
+
+/* ---- fp32 members of the path (north star: "fp32 paths within 1e-4 rel"); NCHW fp32 DEVICE pointers as Tengine lays them out.
+ * Winograd F(4x4, 3x3): 3x3, stride 1, dilation 1, group 1 -- what winograd_support() admits (conv_kernel_x86.c:1896-1915;
+ * kernels wino_conv_kernel_x86.c:126,1118,1291,1376).  weight [Cout][Cin][3][3], bias [Cout] or NULL, activation as
+ * conv_param.activation (-1 none, 0 ReLU, n > 0 clip to [0, n]).  workspace: tb200k_conv_winograd43_f32_workspace() bytes. */
+TB200_API size_t tb200k_conv_winograd43_f32_workspace(const tb200k_conv_shape* s);
+TB200_API int tb200k_conv_winograd43_f32(const float* in, const float* weight, const float* bias, float* out, const tb200k_conv_shape* s, int activation,
+                                         void* workspace, void* stream);
+/* fp32 depthwise 3x3, stride 1 / 2 (conv_dw_kernel_x86.c:2524 conv_dw_run): weight [C][3][3] */
+TB200_API int tb200k_conv_dw3x3_f32(const float* in, const float* weight, const float* bias, float* out, const tb200k_conv_shape* s, int activation,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,35 @@ def run_tmfile(ref, path, x, out_shapes, device=None, precision=3, threads=8, wa
     return outs, (stats[0], stats[1])
 
 
+def conv_f32(ref, x, w, bias, stride=1, pad=0, group=1, activation=-1, threads=8, env=None):
+    """One fp32 convolution on the reference CPU device (Winograd F(4,3) where winograd_support() admits it, im2col + sgemm
+    or the fp32 depthwise kernels otherwise).  x [n,c,h,w], w [oc,c/group,kh,kw] float32.  env e.g. {"TG_DEBUG_REF": "1"}."""
+    x, w = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(w, np.float32)
+    n, c, h, wd = x.shape
+    oc, _, kh, kw = w.shape
+    oh, ow = (h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kw) // stride + 1
+    y = np.zeros((n, oc, oh, ow), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    saved = {}
+    for k, v in (env or {}).items():
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        ref.lib.ref_shim_conv_f32.restype = C.c_int
+        rc = ref.lib.ref_shim_conv_f32(n, c, h, wd, oc, kh, kw, int(stride), int(pad), int(group), int(activation), C.c_void_p(x.ctypes.data),
+                                       C.c_void_p(w.ctypes.data), C.c_void_p(b.ctypes.data) if b is not None else None, C.c_void_p(y.ctypes.data),
+                                       int(threads))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if rc != 0:
+        raise RuntimeError(f"reference fp32 conv failed rc={rc}")
+    return y
+
+
 def save_tmfile(ref, g, path):
     """Write GraphDef `g` as a Tengine tmfile with the reference's own writer (tools/save_graph/save_graph.cpp)."""
     T, L = g.c_tables()

@@ -435,6 +435,70 @@ SHIM_API int ref_shim_save_tmfile(const tb200_tensor_desc* tensors, int num_tens
 
 SHIM_API const char* ref_shim_version(void) { return get_tengine_version(); }
 
+/* One fp32 convolution on the reference CPU device (TENGINE_MODE_FP32): the fp32 members of the path -- Winograd F(4,3)
+ * (wino_conv_hcl, selected by winograd_support(), conv_kernel_x86.c:1896-1915), im2col + sgemm_fp, fp32 depthwise
+ * (conv_dw_kernel_x86.c).  Built the way tests/op/test_op.h:619-664 builds 1-op graphs.  x [n,c,h,w], wt [oc,c/group,kh,kw]. */
+SHIM_API int ref_shim_conv_f32(int n, int c, int h, int w, int oc, int kh, int kw, int stride, int pad, int group, int activation, const float* x,
+                               const float* wt, const float* bias, float* y, int num_thread)
+{
+    if (!g_inited)
+    {
+        if (init_tengine() != 0) return -100;
+        g_inited = 1;
+    }
+    int rc = -1;
+    graph_t graph = create_graph(NULL, NULL, NULL);
+    if (!graph) return -102;
+    node_t in_node = create_graph_node(graph, "in", "InputOp");
+    tensor_t in_t = create_graph_tensor(graph, "in", TENGINE_DT_FP32);
+    set_node_output_tensor(in_node, 0, in_t, TENSOR_TYPE_INPUT);
+    int dims[4] = {n, c, h, w};
+    set_tensor_shape(in_t, dims, 4);
+    int wdims[4] = {oc, c / group, kh, kw};
+    node_t wn = create_graph_node(graph, "w", "Const");
+    tensor_t wtn = create_graph_tensor(graph, "w", TENGINE_DT_FP32);
+    set_node_output_tensor(wn, 0, wtn, TENSOR_TYPE_CONST);
+    set_tensor_shape(wtn, wdims, 4);
+    set_tensor_buffer(wtn, (void*)wt, oc * (c / group) * kh * kw * 4);
+    tensor_t btn = NULL;
+    if (bias)
+    {
+        node_t bn = create_graph_node(graph, "b", "Const");
+        btn = create_graph_tensor(graph, "b", TENGINE_DT_FP32);
+        set_node_output_tensor(bn, 0, btn, TENSOR_TYPE_CONST);
+        int bd[1] = {oc};
+        set_tensor_shape(btn, bd, 1);
+        set_tensor_buffer(btn, (void*)bias, oc * 4);
+    }
+    struct node* node = (struct node*)create_graph_node(graph, "conv", "Convolution");
+    tensor_t out_t = create_graph_tensor(graph, "conv", TENGINE_DT_FP32);
+    set_node_input_tensor(node, 0, in_t);
+    set_node_input_tensor(node, 1, wtn);
+    if (btn) set_node_input_tensor(node, 2, btn);
+    set_node_output_tensor(node, 0, out_t, TENSOR_TYPE_VAR);
+    struct conv_param* p = (struct conv_param*)node->op.param_mem;
+    p->kernel_h = kh, p->kernel_w = kw, p->stride_h = p->stride_w = stride, p->pad_h0 = p->pad_h1 = p->pad_w0 = p->pad_w1 = pad;
+    p->dilation_h = p->dilation_w = 1, p->input_channel = c, p->output_channel = oc, p->group = group, p->activation = activation;
+    const char* in_names[1] = {"in"};
+    const char* out_names[1] = {"conv"};
+    if (set_graph_input_node(graph, in_names, 1) < 0 || set_graph_output_node(graph, out_names, 1) < 0) goto done;
+    set_tensor_buffer(in_t, (void*)x, n * c * h * w * 4);
+    struct options opt;
+    opt.num_thread = num_thread, opt.cluster = TENGINE_CLUSTER_ALL, opt.precision = TENGINE_MODE_FP32, opt.affinity = 0;
+    if (prerun_graph_multithread(graph, opt) < 0) { rc = -103; goto done; }
+    if (run_graph(graph, 1) < 0) { rc = -105; postrun_graph(graph); goto done; }
+    {
+        int od[4];
+        get_tensor_shape(out_t, od, 4);
+        memcpy(y, get_tensor_buffer(out_t), (size_t)od[0] * od[1] * od[2] * od[3] * 4);
+    }
+    postrun_graph(graph);
+    rc = 0;
+done:
+    destroy_graph(graph);
+    return rc;
+}
+
 /* Load a tmfile with the reference's serializer and run it on a named device ("CPU" / NULL, or e.g. "B200") exactly the way
  * tm_benchmark does (create_context + set_context_device + create_graph + set_tensor_shape/buffer + prerun_graph_multithread +
  * run_graph, benchmark/tm_benchmark.cc:60-135), with a caller-supplied NCHW input of `batch` images; copies graph output i

@@ -34,6 +34,7 @@ struct WindowArgs
     int n, c, h, w_in, oh, ow, ocp, oc, stride, ph, pw;
     unsigned ntiles;
     int tiles_w, tiles_h;
+    uint32_t tw_magic, th_magic; // floor(2^32 / d) + 1: q = umulhi(x, magic) is x / d for the tile counts that occur (checked by the launcher)
     uint32_t idesc, tmem_cols;
     int box_w, box_h, xoff, in_bytes, ks;
     uint32_t fill; // uint8: the input zero point replicated x4 (0 for int8: the TMA zero fill already is the padding)
@@ -71,9 +72,10 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
     __syncthreads();
     auto tile_coords = [&](unsigned tile, int& n, int& oh0, int& ow0)
     {
-        const unsigned r = tile / (unsigned)a.tiles_w;
+        // two divisions by launch constants as multiply-high (a 32-bit division costs ~40 instructions and this runs per tile)
+        const unsigned r = a.tw_magic ? __umulhi(tile, a.tw_magic) : tile; // magic 0: divisor 1
         ow0 = (int)(tile - r * a.tiles_w) * 16;
-        n = (int)(r / (unsigned)a.tiles_h);
+        n = (int)(a.th_magic ? __umulhi(r, a.th_magic) : r);
         oh0 = (int)(r - (unsigned)n * a.tiles_h) * 8;
     };
     // (a macro, not a lambda: the tensor map must be addressed as the kernel parameter itself)
@@ -222,28 +224,64 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
             uint32_t w[4];
             if (U8)
             {
-                int32_t acc[16];
-                float bt[16];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    const float4 p01 = lds_f4(sPar + c * 8 + j * 32), p23 = lds_f4(sPar + c * 8 + j * 32 + 16);
-                    // (bias term, corr[oc]) per channel: corr = -zx*sum(w) + K*zx*zw travels in the .y lanes
-                    acc[j * 4 + 0] = (int32_t)v[j * 4 + 0] + rowc + __float_as_int(p01.y), acc[j * 4 + 1] = (int32_t)v[j * 4 + 1] + rowc + __float_as_int(p01.w);
-                    acc[j * 4 + 2] = (int32_t)v[j * 4 + 2] + rowc + __float_as_int(p23.y), acc[j * 4 + 3] = (int32_t)v[j * 4 + 3] + rowc + __float_as_int(p23.w);
-                    bt[j * 4 + 0] = p01.x, bt[j * 4 + 1] = p01.z, bt[j * 4 + 2] = p23.x, bt[j * 4 + 3] = p23.z;
-                }
+                // the int8 form (engine.cu: constants { M, M, y, y } with y = corr[oc] + bias[oc]): a' = v - zw*sum(x) + y, t = fl(a' * M)
                 if (MODE == 2)
                 {
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
                         if ((k & 3) == 0) w[k >> 2] = 0;
-                        if (c + k < a.oc) w[k >> 2] |= ((uint32_t)requant(acc[k], c + k, e) & 0xffu) << (8 * (k & 3));
+                        if (c + k < a.oc)
+                        {
+                            const float4 pp = lds_f4(sPar + c * 8 + (k >> 1) * 16);
+                            const int32_t acc = (int32_t)v[k] + rowc + __float_as_int((k & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + c + k) : 0);
+                            w[k >> 2] |= ((uint32_t)requant(acc, c + k, e) & 0xffu) << (8 * (k & 3));
+                        }
                     }
                 }
                 else
-                    requant_unit16_u8(acc, bt, c, a.oc, e, w);
+                {
+                    float gw[4];
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                    {
+                        float4 p[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) p[k] = lds_f4(sPar + c * 8 + h * 64 + k * 16);
+                        int32_t a8[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) a8[k] = (int32_t)v[h * 8 + k] + rowc;
+                        requant_fast8_i8<false>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
+                    }
+                    if (e.q_byte_add)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
+                    }
+                    if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (gw[j] > 0.5f - TB200_TIE_EPS)
+                            {
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                {
+                                    const int oc = c + j * 4 + t;
+                                    const float4 pp = lds_f4(sPar + c * 8 + ((j * 4 + t) >> 1) * 16);
+                                    const int32_t acc = (int32_t)v[j * 4 + t] + rowc + __float_as_int((t & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + oc) : 0);
+                                    if (oc < a.oc) w[j] = requant_fix_byte(w[j], t, acc, oc, e);
+                                }
+                            }
+                    }
+                    if (c + 16 > a.oc)
+                    {
+                        // pad lanes of uint8 tensors hold 0, not the zero point
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if (c + k >= a.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3)));
+                    }
+                }
             }
             else if (MODE == 2)
             {
@@ -323,6 +361,10 @@ cudaError_t launch_conv_window(const WindowPlan& p, const void* w, void* out, co
     a.n = s.n, a.c = s.c, a.h = s.h, a.w_in = s.w, a.oh = s.oh, a.ow = s.ow, a.ocp = s.ocp, a.oc = s.oc, a.stride = s.sh, a.ph = s.ph0, a.pw = s.pw0;
     a.tiles_w = (s.ow + 15) / 16, a.tiles_h = (s.oh + 7) / 8;
     a.ntiles = (unsigned)((long long)a.tiles_w * a.tiles_h * s.n);
+    // umulhi(x, floor(2^32/d) + 1) == x / d whenever x * d < 2^32 (error term x * (d - 2^32 mod d) / (d * 2^32) < 1 / d)
+    if ((unsigned long long)a.ntiles * (unsigned)a.tiles_w >= (1ull << 32) || (unsigned long long)a.ntiles * (unsigned)a.tiles_h >= (1ull << 32)) return cudaErrorInvalidValue;
+    a.tw_magic = a.tiles_w == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned)a.tiles_w) + 1u;
+    a.th_magic = a.tiles_h == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned)a.tiles_h) + 1u;
     a.idesc = make_idesc_i8(s.ocp, !e.is_uint8, !e.is_uint8);
     uint32_t cols = 32;
     while (cols < (uint32_t)s.ocp) cols <<= 1;

@@ -6,11 +6,13 @@
 // analogue of cpu_device.c:97-221 with every node executing on the GPU.  No CPU compute path exists here.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +26,17 @@
 using namespace tb200;
 
 #define TB200_OP_NOP_ (-1) // planner-internal: a node folded into its producer
+#define TB200_PACK_FORMAT 3  // bump whenever the layout of the packed weight arena changes (pack cache key)
+
+// ---- packed-weight cache directory: tb200_pack_cache_dir() or the environment ----
+static std::string g_pack_cache_dir;
+static bool g_pack_cache_set = false;
+static std::string pack_cache_dir()
+{
+    if (g_pack_cache_set) return g_pack_cache_dir;
+    const char* e = getenv("TG_B200_PACK_CACHE");
+    return e ? std::string(e) : std::string();
+}
 
 // ---- error reporting -------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -193,6 +206,7 @@ struct tb200_graph
     std::vector<tb200_graph*> shards;
     int first_image = 0, num_images = 0, total_images = 0;
     size_t act_unshared_bytes = 0; // what the arena would need without slot reuse (introspection)
+    int pack_cache_state = 0;      // 0 no cache directory, 1 packed and written, 2 read from the cache
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -419,7 +433,7 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
 static size_t gemm_weight_bytes(int ocp, int k, bool u8)
 {
     const int bn = gemm_block_n(ocp, u8), nt = (ocp + bn - 1) / bn;
-    return (size_t)nt * (bn + (u8 ? 16 : 0)) * k;
+    return (size_t)nt * bn * k;
 }
 
 struct WeightBlob
@@ -716,8 +730,8 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             blobs[li].fast_off = wtotal;
             wtotal += align_up((size_t)tout.cp * 8, 256);
             blobs[li].btab_off = wtotal;
-            if (u8 && (kind[li] == K_GEMM || kind[li] == K_IGEMM))
-                wtotal += align_up((size_t)(L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w) * tout.cp * 4, 256);
+            if (u8 && kind[li] == K_IGEMM) // [border patterns][OCp] int32, see the packing below
+                wtotal += align_up((size_t)(L.pad_h0 + 1) * (L.kernel_h + 1) * (L.pad_w0 + 1) * (L.kernel_w + 1) * tout.cp * 4, 256);
         }
         if (kind[li] == K_LUT)
         {
@@ -849,6 +863,25 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
         }
         fuse_bias[li] = fuse ? 1 : 0;
     }
+    // ---- uint8 tensor-core layers use the int8 form of the fast epilogue: t = fl((float)(acc_true + bias) * M), M = fl(s_in*s_w/s_out).
+    //      The reference forms f = fl(fl(acc*S) + fl(bias*S)) and t_ref = fl(f / s_out): |t - t_ref| <= 2^-24 (2|bias*M| + 5|t|), which
+    //      stays inside the 2^-13 tie guard for every in-range t (|t| <= 255) as long as |bias*M| <= 250 -- checked here per channel;
+    //      an FC whose bias tensor carries its own scale (fc_ref.c:141-146) cannot fold the bias into the integer sum at all.
+    //      Layers that fail the check take the exact epilogue. ----
+    std::vector<int> u8_tc_fast(num_layers, 1);
+    for (int li = 0; li < num_layers; li++)
+    {
+        const tb200_layer_desc& L = layers[li];
+        if ((L.op != TB200_OP_CONV && L.op != TB200_OP_FC) || (kind[li] != K_GEMM && kind[li] != K_IGEMM && kind[li] != K_GATHER_TC)) continue;
+        const TensorInfo& tin = g->tensors[L.inputs[0]];
+        const TensorInfo& tout = g->tensors[L.output];
+        if (tin.d.data_type != TB200_DT_UINT8) continue;
+        const float S = tin.d.scale * L.weight_scales[0];
+        if (L.op == TB200_OP_FC && L.bias && L.bias_scale != 0.f && L.bias_scale != S) u8_tc_fast[li] = 0;
+        const double M = (double)tin.d.scale * (double)L.weight_scales[0] / (double)tout.d.scale;
+        for (int o = 0; o < tout.d.dims[1] && L.bias; o++)
+            if (!(fabs((double)L.bias[o] * M) <= 250.0)) u8_tc_fast[li] = 0;
+    }
     // ---- int8 fast epilogue rounds BEFORE it clamps (integer-domain clamp on 16-bit lanes, common.cuh): prove from the
     //      weights that no reachable accumulator can leave the 16-bit range after scaling, else use the exact path ----
     std::vector<int> fast_int_ok(num_layers, 1);
@@ -876,11 +909,64 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
         }
     }
 
-    // ---- pack weights into a host image of the arena, one H2D copy ----
+    // ---- pack weights into a host image of the arena, one H2D copy.  With a pack cache directory (tb200_pack_cache_dir /
+    //      TG_B200_PACK_CACHE) the image is keyed by a hash of everything it depends on -- descriptors, kernel
+    //      choices, weights, biases, scales -- and a second prerun of the same model reads it back instead of packing again
+    //      (the analogue of keeping conv_hcl_prerun's interleaved weights, conv_kernel_x86.c:2137-2209, next to the tmfile). ----
     if (!(flags & TB200_PRERUN_NO_WEIGHTS))
     {
         std::vector<uint8_t> img(g->w_bytes, 0);
-        for (int li = 0; li < num_layers; li++)
+        std::string cache_path;
+        bool cache_hit = false;
+        uint64_t cache_hash = 0;
+        {
+            const std::string dir = pack_cache_dir();
+            if (!dir.empty())
+            {
+                uint64_t h = 1469598103934665603ull;
+                auto mix = [&](const void* p, size_t n)
+                {
+                    const uint8_t* b = (const uint8_t*)p;
+                    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+                };
+                const int ver = TB200_PACK_FORMAT;
+                mix(&ver, sizeof ver), mix(&g->w_bytes, sizeof g->w_bytes), mix(&num_layers, sizeof num_layers);
+                for (int li = 0; li < num_layers; li++)
+                {
+                    const tb200_layer_desc& L = layers[li];
+                    mix(&kind[li], sizeof(int)), mix(&blobs[li], sizeof(WeightBlob)), mix(&fuse_bias[li], sizeof(int));
+                    mix(&L.op, offsetof(tb200_layer_desc, weight)); // every scalar field up to the pointers
+                    mix(&L.weight_zero, sizeof L.weight_zero), mix(&L.bias_scale, sizeof L.bias_scale);
+                    for (int k = 0; k < L.num_inputs && k < 4; k++) mix(&g->tensors[L.inputs[k]].d, sizeof(tb200_tensor_desc));
+                    if (L.op != TB200_OP_NOP_) mix(&g->tensors[L.output].d, sizeof(tb200_tensor_desc));
+                    if (L.op == TB200_OP_CONV || L.op == TB200_OP_FC)
+                    {
+                        const TensorInfo& ti = g->tensors[L.inputs[0]];
+                        const TensorInfo& to = g->tensors[L.output];
+                        const size_t kk = L.op == TB200_OP_FC ? (size_t)ti.d.dims[1] * ti.d.dims[2] * ti.d.dims[3]
+                                                              : (size_t)(ti.d.dims[1] / L.group) * L.kernel_h * L.kernel_w;
+                        mix(L.weight, (size_t)to.d.dims[1] * kk);
+                        if (L.bias) mix(L.bias, (size_t)to.d.dims[1] * 4);
+                        mix(L.weight_scales, ti.d.data_type == TB200_DT_UINT8 ? 4 : (size_t)to.d.dims[1] * 4);
+                    }
+                }
+                // batch-dependent fields of the tensor descriptors were hashed too: a cache entry is per (model, batch) like a plan
+                char name[64];
+                snprintf(name, sizeof name, "/tb200_%016llx.pack", (unsigned long long)h);
+                cache_path = dir + name;
+                cache_hash = h;
+                if (FILE* f = fopen(cache_path.c_str(), "rb"))
+                {
+                    uint64_t hdr[3] = {0, 0, 0};
+                    if (fread(hdr, sizeof hdr, 1, f) == 1 && hdr[0] == 0x3032424b43415054ull + TB200_PACK_FORMAT && hdr[1] == h && hdr[2] == g->w_bytes &&
+                        fread(img.data(), 1, g->w_bytes, f) == g->w_bytes)
+                        cache_hit = true;
+                    fclose(f);
+                }
+            }
+        }
+        g->pack_cache_state = cache_path.empty() ? 0 : (cache_hit ? 2 : 1);
+        for (int li = 0; li < num_layers && !cache_hit; li++)
         {
             const tb200_layer_desc& L = layers[li];
             if (kind[li] == K_LUT)
@@ -898,7 +984,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             uint8_t* dst = img.data() + blobs[li].w_off;
             const bool tc = kind[li] == K_GEMM || kind[li] == K_IGEMM;
             // row of output channel o in the packed B operand (uint8 tensor-core tiles carry 16 extra rows each)
-            const int bn = tc ? gemm_block_n(tout.cp, u8) : tout.cp, bnx = bn + ((tc && u8) ? 16 : 0);
+            const int bn = tc ? gemm_block_n(tout.cp, u8) : tout.cp, bnx = bn;
             auto brow = [&](int o) -> size_t { return (size_t)(o / bn) * bnx + (o % bn); };
             size_t krow = 0; // K extent of one packed row
             if (L.op == TB200_OP_FC)
@@ -944,13 +1030,30 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             std::vector<int64_t> wsum_tot(tout.cp, 0); // uint8 tensor-core kinds: sum of the raw weight bytes per channel
             if (tc && u8)
             {
-                // ones-row of every N tile: accumulator column block_n becomes sum_k x of the pixel
-                const int nt = (tout.cp + bn - 1) / bn;
-                for (int t = 0; t < nt; t++) memset(dst + ((size_t)t * bnx + bn) * krow, 1, krow);
-                // pad K positions (channels >= C) of the ones-row must not count: x is 0 there anyway (pad lanes hold 0)
+                // the tensor cores form sum x*(w - zw) themselves: B = w - 128 as int8 (plus a constant tile of 128 - zw in the kernel),
+                // or plain w when zw == 0.  Real K positions only; pad positions stay 0 (x is 0 there anyway).
+                if (L.weight_zero != 0)
+                {
+                    const size_t kreal_row = krow; // bytes per packed row
+                    for (int o = 0; o < OC; o++)
+                    {
+                        uint8_t* row = dst + brow(o) * kreal_row;
+                        if (L.op == TB200_OP_FC)
+                        {
+                            for (int c = 0; c < C; c++)
+                                for (int p2 = 0; p2 < H * W; p2++) row[(size_t)p2 * tin.cp + c] = (uint8_t)(int8_t)((int)row[(size_t)p2 * tin.cp + c] - 128);
+                        }
+                        else
+                        {
+                            const int KT = L.kernel_h * L.kernel_w;
+                            for (int t = 0; t < KT; t++)
+                                for (int c = 0; c < C; c++) row[(size_t)t * tin.cp + c] = (uint8_t)(int8_t)((int)row[(size_t)t * tin.cp + c] - 128);
+                        }
+                    }
+                }
                 const int taps = L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w;
                 const int kk = L.op == TB200_OP_FC ? C * H * W : C; // real K elements per tap
-                int32_t* bt = (int32_t*)(img.data() + blobs[li].btab_off);
+                std::vector<int64_t> tapc((size_t)taps * OC, 0); // what a tap that falls into the padding must give back: zx*(sum_c w - Cin*zw)
                 for (int o = 0; o < OC; o++)
                     for (int t = 0; t < taps; t++)
                     {
@@ -960,9 +1063,32 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                         else
                             for (int c = 0; c < C; c++) sw += src[((size_t)o * C + c) * taps + t];
                         wsum_tot[o] += sw;
-                        // what a tap that falls into the padding must give back: zx*(sum_c w - Cin*zw)
-                        bt[(size_t)t * tout.cp + o] = (int32_t)((int64_t)tin.d.zero_point * (sw - (int64_t)kk * L.weight_zero));
+                        tapc[(size_t)t * OC + o] = (int64_t)tin.d.zero_point * (sw - (int64_t)kk * L.weight_zero);
                     }
+                if (kind[li] == K_IGEMM)
+                {
+                    // Border patterns: a pixel whose window is cut by a rows at the top, b at the bottom, c columns on the left and d on
+                    // the right misses the taps {kh < a or kh >= KH-b or kw < c or kw >= KW-d}; the table holds the SUM of their
+                    // corrections per channel, index ((a*(KH+1) + b)*(pw+1) + c)*(KW+1) + d (gemm_tcgen05.cu border_pattern), so a
+                    // border row costs one vector load per four channels instead of a loop over taps.
+                    const int KH = L.kernel_h, KW = L.kernel_w;
+                    int32_t* pt = (int32_t*)(img.data() + blobs[li].btab_off);
+                    for (int a = 0; a <= L.pad_h0; a++)
+                        for (int b2 = 0; b2 <= KH; b2++)
+                            for (int c2 = 0; c2 <= L.pad_w0; c2++)
+                                for (int d2 = 0; d2 <= KW; d2++)
+                                {
+                                    const size_t pid = (((size_t)a * (KH + 1) + b2) * (L.pad_w0 + 1) + c2) * (KW + 1) + d2;
+                                    for (int o = 0; o < OC; o++)
+                                    {
+                                        int64_t sum = 0;
+                                        for (int kh = 0; kh < KH; kh++)
+                                            for (int kw = 0; kw < KW; kw++)
+                                                if (kh < a || kh >= KH - b2 || kw < c2 || kw >= KW - d2) sum += tapc[(size_t)(kh * KW + kw) * OC + o];
+                                        pt[pid * tout.cp + o] = (int32_t)sum;
+                                    }
+                                }
+                }
             }
             if (kind[li] == K_GATHER_TC && u8)
             {
@@ -979,7 +1105,22 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             {
                 b[o] = (L.bias && o < OC) ? L.bias[o] : 0;
                 sc[o] = u8 ? L.weight_scales[0] : (o < OC ? L.weight_scales[o] : 1.f);
-                if (u8)
+                if (u8 && (tc || kind[li] == K_GATHER_TC))
+                {
+                    // tensor-core layers: the int8 layout { M[2k], M[2k+1], y[2k], y[2k+1] } with y = corr[oc] + bias[oc] as an integer
+                    // (corr[oc] = -zx*sum_k w + K*zx*zw: what the zero points contribute when every tap is inside the image)
+                    float* fmM = fm + (size_t)(o >> 1) * 4 + (o & 1);
+                    float* fmY = fmM + 2;
+                    int32_t y = 0;
+                    if (o < OC)
+                    {
+                        const int64_t kreal = fc ? (int64_t)C * H * W : (int64_t)C * L.kernel_h * L.kernel_w;
+                        y = (int32_t)(-(int64_t)tin.d.zero_point * wsum_tot[o] + kreal * tin.d.zero_point * L.weight_zero + (int64_t)b[o]);
+                    }
+                    *fmM = (o >= OC) ? 0.f : (float)((double)tin.d.scale * (double)L.weight_scales[0] / (double)tout.d.scale);
+                    memcpy(fmY, &y, 4);
+                }
+                else if (u8)
                 {
                     // the bias term in real units, rounded exactly as the reference rounds it
                     const float S = tin.d.scale * L.weight_scales[0];
@@ -1006,6 +1147,36 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     if (fuse) *fmY = (o >= OC) ? 0.f : (float)((double)b[o] * (double)*fmM); // fl(bias*M)
                     else memcpy(fmY, &b[o], 4);
                 }
+            }
+        }
+        if (getenv("TB200_DEBUG_HASH") && atoi(getenv("TB200_DEBUG_HASH")) >= 2)
+        {
+            auto fnv = [](const void* p, size_t n) {
+                uint64_t h = 1469598103934665603ull;
+                for (size_t i = 0; i < n; i++) h = (h ^ ((const uint8_t*)p)[i]) * 1099511628211ull;
+                return (unsigned long long)h;
+            };
+            for (int li = 0; li < num_layers; li++)
+            {
+                const tb200_layer_desc& L = layers[li];
+                if (L.op != TB200_OP_CONV && L.op != TB200_OP_FC) continue;
+                const int ocp = g->tensors[L.output].cp;
+                fprintf(stderr, "[tb200 dbg] pack layer %d kind %d: w %016llx (%zu) bias %016llx scale %016llx fast %016llx fuse %d fast_int %d u8fast %d\n", li, kind[li],
+                        fnv(img.data() + blobs[li].w_off, blobs[li].w_size), blobs[li].w_size, fnv(img.data() + blobs[li].bias_off, (size_t)ocp * 4),
+                        fnv(img.data() + blobs[li].scale_off, (size_t)ocp * 4), fnv(img.data() + blobs[li].fast_off, (size_t)ocp * 8), fuse_bias[li], fast_int_ok[li],
+                        u8_tc_fast[li]);
+            }
+        }
+        if (!cache_path.empty() && !cache_hit)
+        {
+            // write-then-rename so that a concurrent reader never sees a partial file; failure to write is not an error
+            const std::string tmp = cache_path + ".tmp" + std::to_string((long long)getpid());
+            if (FILE* f = fopen(tmp.c_str(), "wb"))
+            {
+                const uint64_t hdr[3] = {0x3032424b43415054ull + TB200_PACK_FORMAT, cache_hash, g->w_bytes};
+                const bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(img.data(), 1, g->w_bytes, f) == g->w_bytes;
+                fclose(f);
+                if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
             }
         }
         CUDA_OK(cudaMemcpyAsync(g->w_arena, img.data(), g->w_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1067,7 +1238,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                 s.epi.fast_par = (const float2*)(g->w_arena + blobs[li].fast_off);
                 s.btab = (const int32_t*)(g->w_arena + blobs[li].btab_off);
                 s.epi.fuse_bias = fuse_bias[li];
-                if (!fast_int_ok[li]) s.epi.fast_ok = 0;
+                if (!fast_int_ok[li] || !u8_tc_fast[li]) s.epi.fast_ok = 0;
                 ConvShape& cs = s.cs;
                 cs.n = N, cs.h = H, cs.w = W, cs.c = C, cs.cp = tin.cp, cs.oh = OH, cs.ow = OW, cs.oc = OC, cs.ocp = tout.cp;
                 if (fc)
@@ -1106,14 +1277,14 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                 if (s.kind == K_CONV_DW && !(flags & TB200_PRERUN_NO_TENSORCORE)) dw_plan_create(&s.dwp, s.in, s.cs, s.epi); // falls back when not applicable
                 if (s.kind == K_IGEMM)
                 {
-                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.out, s.cs, u8 ? 1 : 0);
+                    int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.out, s.cs, u8 ? 1 + L.weight_zero : 0);
                     if (rc) return bail(fail(rc, "layer %d: implicit-GEMM plan failed", li));
                 }
                 if (s.kind == K_GEMM)
                 {
                     const long long m = fc ? N : (long long)N * H * W;
                     const int kdim = fc ? H * W * tin.cp : tin.cp;
-                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, s.out, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 : 0);
+                    int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, s.out, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 + L.weight_zero : 0);
                     if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
                 }
             }
@@ -1437,6 +1608,14 @@ int tb200_graph_broadcast_weights(tb200_graph* g)
     return broadcast_arena(g);
 }
 
+int tb200_pack_cache_dir(const char* dir)
+{
+    g_pack_cache_set = true;
+    g_pack_cache_dir = dir ? dir : "";
+    return 0;
+}
+int tb200_graph_pack_cache_state(tb200_graph* g) { return g ? g->pack_cache_state : 0; }
+
 int tb200_graph_num_shards(tb200_graph* g) { return g ? 1 + (int)g->shards.size() : 0; }
 
 int tb200_graph_shard(tb200_graph* g, int index, int* cuda_device, int* first_image, int* num_images)
@@ -1472,9 +1651,38 @@ int tb200_graph_upload(tb200_graph* g, int input_index, const void* host_nchw)
     return rc;
 }
 
+static unsigned long long debug_fnv(const void* p, size_t n)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ ((const uint8_t*)p)[i]) * 1099511628211ull;
+    return (unsigned long long)h;
+}
+
 static int launch_one(tb200_graph* g)
 {
     CUDA_OK(cudaSetDevice(g->ctx->device));
+    static const int dbg = getenv("TB200_DEBUG_HASH") ? atoi(getenv("TB200_DEBUG_HASH")) : 0;
+    if (dbg >= 2)
+    {
+        // debug: launch by launch, a hash of every layer's output tensor (NHWC bytes) and of the weight arena
+        std::vector<uint8_t> host;
+        host.resize(g->w_bytes);
+        CUDA_OK(cudaMemcpy(host.data(), g->w_arena, g->w_bytes, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tb200 dbg] weight arena %zu bytes hash %016llx\n", g->w_bytes, debug_fnv(host.data(), g->w_bytes));
+        for (const Step& s : g->steps)
+        {
+            int rc = run_step(g, s, g->ctx->stream);
+            if (rc) return rc;
+            CUDA_OK(cudaStreamSynchronize(g->ctx->stream));
+            if (s.layer < 0) continue;
+            const TensorInfo& t = g->tensors[g->layers[s.layer].output];
+            host.resize(t.nhwc_bytes);
+            CUDA_OK(cudaMemcpy(host.data(), t.dev, t.nhwc_bytes, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[tb200 dbg] layer %d %s out [%d %d %d %d] hash %016llx\n", s.layer, kStepName[s.kind], t.d.dims[0], t.d.dims[1], t.d.dims[2], t.d.dims[3],
+                    debug_fnv(host.data(), t.nhwc_bytes));
+        }
+        return 0;
+    }
     if (!g->cu_execs.empty())
     {
         CUDA_OK(cudaGraphLaunch(g->cu_execs[0], g->ctx->stream)); // the whole-batch graph
@@ -1560,7 +1768,8 @@ static int run_enqueue_compute(tb200_graph* g, void* const* host_outputs)
 {
     CUDA_OK(cudaSetDevice(g->ctx->device));
     cudaStream_t cs = g->ctx->stream;
-    if (g->chunks <= 1 || g->cu_execs.empty())
+    static const int dbg2 = getenv("TB200_DEBUG_HASH") ? atoi(getenv("TB200_DEBUG_HASH")) : 0;
+    if (g->chunks <= 1 || g->cu_execs.empty() || dbg2 >= 2)
     {
         int rc = launch_one(g);
         if (rc) return rc;
@@ -1613,6 +1822,22 @@ int tb200_graph_run(tb200_graph* g, const void* const* host_inputs, void* const*
     if (!rc) rc = for_each_shard(g, [&](tb200_graph* sh, int) { return run_enqueue_compute(sh, host_outputs); });
     const int rc2 = for_each_shard(g, [&](tb200_graph* sh, int) { return run_wait(sh); }); // always drain what was queued
     cudaSetDevice(g->ctx->device);
+    static const bool dbg = getenv("TB200_DEBUG_HASH") != nullptr;
+    if (dbg)
+    {
+        auto fnv = [](const void* p, size_t n) {
+            uint64_t h = 1469598103934665603ull;
+            for (size_t i = 0; i < n; i++) h = (h ^ ((const uint8_t*)p)[i]) * 1099511628211ull;
+            return (unsigned long long)h;
+        };
+        for (size_t i = 0; i < g->input_ids.size(); i++)
+            fprintf(stderr, "[tb200 run] input %zu: %zu bytes, hash %016llx\n", i, image_bytes(g, g->input_ids[i]) * (size_t)g->total_images,
+                    fnv(host_inputs[i], image_bytes(g, g->input_ids[i]) * (size_t)g->total_images));
+        for (size_t i = 0; i < g->output_ids.size(); i++)
+            fprintf(stderr, "[tb200 run] output %zu (tensor %d): %zu bytes, hash %016llx\n", i, g->output_ids[i], image_bytes(g, g->output_ids[i]) * (size_t)g->total_images,
+                    fnv(host_outputs[i], image_bytes(g, g->output_ids[i]) * (size_t)g->total_images));
+        fprintf(stderr, "[tb200 run] %zu layers, %d launches, chunks %d, shards %zu, flags %d\n", g->layers.size(), g->num_launches, g->chunks, g->shards.size() + 1, g->flags);
+    }
     return rc ? rc : rc2;
 }
 
@@ -1701,6 +1926,82 @@ int tb200_graph_profile(tb200_graph* g, float* layer_ms, int num_layers)
     return rc;
 }
 
+// Tables of the per-byte functions of the example's post-processing, with its own arithmetic: dequantisation
+// ((float)q - zp) * scale (tm_yolov3_tiny_uint8.cpp:471-478), sigmoid = (float)(1.f / (1.f + exp(-x))) with the C library's double
+// exp() (:46-49), and exp(x) kept in double because `float pred_w = exp(dw) * anchor_w` multiplies before narrowing (:230).
+static void build_yolo_tables(const tb200_tensor_desc& d, float* sig, double* ex)
+{
+    for (int b = 0; b < 256; b++)
+    {
+        const float q = d.data_type == TB200_DT_UINT8 ? (float)b : (float)(int)(int8_t)b;
+        volatile float x = (q - (float)d.zero_point) * d.scale;
+        sig[b] = (float)(1.f / (1.f + exp((double)-x)));
+        ex[b] = exp((double)x);
+    }
+}
+
+int tb200_graph_yolo_detect(tb200_graph* g, const tb200_yolo_params* p, tb200_detection* out, int max_per_image, int32_t* counts)
+{
+    if (!g || !p || !out || !counts || max_per_image < 1 || p->num_heads < 1 || p->num_heads > 3) return fail(TB200_ERR_INVALID, "bad arguments");
+    const int max_cand = p->max_candidates > 0 ? p->max_candidates : 4096;
+    static_assert(sizeof(YoloDet) == sizeof(tb200_detection), "detection record layout");
+    const int rc = for_each_shard(g, [&](tb200_graph* sh, int) -> int {
+        CUDA_OK(cudaSetDevice(sh->ctx->device));
+        cudaStream_t st = sh->ctx->stream;
+        const int n_img = sh->num_images;
+        YoloCand *cand = nullptr, *sorted = nullptr;
+        YoloDet* det = nullptr;
+        int *cnt = nullptr, *ocnt = nullptr;
+        float* sig = nullptr;
+        double* ex = nullptr;
+        auto cleanup = [&]() { cudaFree(cand), cudaFree(sorted), cudaFree(det), cudaFree(cnt), cudaFree(ocnt), cudaFree(sig), cudaFree(ex); };
+        cudaError_t e = cudaMalloc(&cand, sizeof(YoloCand) * (size_t)n_img * max_cand);
+        if (e == cudaSuccess) e = cudaMalloc(&sorted, sizeof(YoloCand) * (size_t)n_img * max_cand);
+        if (e == cudaSuccess) e = cudaMalloc(&det, sizeof(YoloDet) * (size_t)n_img * max_per_image);
+        if (e == cudaSuccess) e = cudaMalloc(&cnt, sizeof(int) * n_img);
+        if (e == cudaSuccess) e = cudaMalloc(&ocnt, sizeof(int) * n_img);
+        if (e == cudaSuccess) e = cudaMalloc(&sig, sizeof(float) * 256 * 3);
+        if (e == cudaSuccess) e = cudaMalloc(&ex, sizeof(double) * 256 * 3);
+        if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(int) * n_img, st);
+        unsigned key_base = 0;
+        for (int hd = 0; hd < p->num_heads && e == cudaSuccess; hd++)
+        {
+            const tb200_yolo_head& H = p->heads[hd];
+            if (H.output_index < 0 || H.output_index >= (int)sh->output_ids.size())
+            {
+                cleanup();
+                return fail(TB200_ERR_INVALID, "yolo head %d: output index %d", hd, H.output_index);
+            }
+            const TensorInfo& t = sh->tensors[sh->output_ids[H.output_index]];
+            if (t.d.dims[1] != 3 * (p->num_classes + 5))
+            {
+                cleanup();
+                return fail(TB200_ERR_INVALID, "yolo head %d: %d channels, expected 3 x (5 + %d)", hd, t.d.dims[1], p->num_classes);
+            }
+            float hs[256];
+            double he[256];
+            build_yolo_tables(t.d, hs, he);
+            e = cudaMemcpyAsync(sig + hd * 256, hs, sizeof hs, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ex + hd * 256, he, sizeof he, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st); // hs / he live on this stack frame
+            if (e == cudaSuccess)
+                e = launch_yolo_decode(t.dev, t.cp, t.d.dims[2], t.d.dims[3], n_img, 3, p->num_classes, sig + hd * 256, ex + hd * 256, (float)H.stride, H.anchors,
+                                       p->prob_threshold, cand, cnt, max_cand, key_base, t.d.data_type == TB200_DT_UINT8, st);
+            key_base += (unsigned)(t.d.dims[2] * t.d.dims[3] * 3);
+        }
+        if (e == cudaSuccess) e = launch_yolo_nms(cand, cnt, n_img, max_cand, p->nms_threshold, sorted, det, max_per_image, ocnt, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out + (size_t)sh->first_image * max_per_image, det, sizeof(YoloDet) * (size_t)n_img * max_per_image, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts + sh->first_image, ocnt, sizeof(int) * n_img, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cleanup();
+        if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "yolo_detect: %s", cudaGetErrorString(e));
+        return 0;
+    });
+    cudaSetDevice(g->ctx->device);
+    return rc;
+}
+
 int tb200_graph_work(tb200_graph* g, double* ops, double* bytes)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
@@ -1770,6 +2071,21 @@ int tb200k_gemm_i8(const void* in, const void* weight, void* out, int64_t m, int
     if (rc) return fail(rc, "gemm plan failed");
     EpiParams p = epi_from_abi(e);
     K_LAUNCH(launch_gemm_i8(plan, p, nullptr, sms, (cudaStream_t)stream));
+}
+size_t tb200k_conv_winograd43_f32_workspace(const tb200k_conv_shape* s) { return s ? wino43_workspace_bytes(s->n, s->c, s->oc, s->oh, s->ow) : 0; }
+int tb200k_conv_winograd43_f32(const float* in, const float* weight, const float* bias, float* out, const tb200k_conv_shape* s, int activation, void* workspace,
+                               void* stream)
+{
+    K_CHECK(in && weight && out && s && workspace && s->kh == 3 && s->kw == 3 && s->sh == 1 && s->sw == 1 && s->dh == 1 && s->dw == 1 && s->group == 1);
+    K_CHECK(s->oh == s->h + 2 * s->ph0 - 2 && s->ow == s->w + 2 * s->pw0 - 2);
+    K_LAUNCH(launch_conv_winograd43_f32(in, weight, bias, out, s->n, s->c, s->h, s->w, s->oc, s->oh, s->ow, s->ph0, s->pw0, activation, (float*)workspace,
+                                        (cudaStream_t)stream));
+}
+int tb200k_conv_dw3x3_f32(const float* in, const float* weight, const float* bias, float* out, const tb200k_conv_shape* s, int activation, void* stream)
+{
+    K_CHECK(in && weight && out && s && s->kh == 3 && s->kw == 3 && s->sh == s->sw && (s->sh == 1 || s->sh == 2) && s->dh == 1 && s->dw == 1 &&
+            s->group == s->c && s->oc == s->c);
+    K_LAUNCH(launch_conv_dw3x3_f32(in, weight, bias, out, s->n, s->c, s->h, s->w, s->oh, s->ow, s->sh, s->ph0, s->pw0, activation, (cudaStream_t)stream));
 }
 int tb200k_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, void* stream)
 {

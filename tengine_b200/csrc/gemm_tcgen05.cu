@@ -62,8 +62,10 @@ struct GemmArgs
     int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp;
     int bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
     uint32_t a_tx_bytes; // bytes one A load delivers (block_k * rows of the patch)
-    // uint8: the B tile carries 16 extra rows, row block_n = all ones, so accumulator column block_n = sum_k x (per pixel)
-    int u8, bnx, taps, in_h, in_w;
+    // uint8 (unsigned A): sum x*(w - zw) is formed ON the tensor cores.  B holds w - 128 as int8 and a second MMA per k-step
+    // multiplies the same A tile with a constant tile of value 128 - zw (cplane; 0: not needed, zw == 128 -- or zw == 0, where B
+    // simply stays unsigned): x*(w-128) + x*(128-zw) = x*(w-zw), exact, no per-pixel sum of x, no extra accumulator column.
+    int u8, bnx, taps, in_h, in_w, b_signed, cplane;
     // epilogue / stores
     int cs, ngroups; // 16-column chunks per store group (1, 2 or 4) and groups per m-tile
     int rows_valid;  // rows of an m-tile that are output pixels (128, or bw*bh*bn of a smaller conv patch)
@@ -71,7 +73,7 @@ struct GemmArgs
     int par_all;     // the constants of every channel are resident (loaded once); else reloaded per N tile
     int b_res;       // the N tile's weights (all k-blocks) are loaded once and stay in smem; the ring carries A only
     int teams;       // the epilogue warps form two teams, one per accumulator stage (see the epilogue)
-    const int32_t* btab; // [taps][OCp]: zx * (sum_c w[oc][tap][c] - Cin*zw), the correction a padding tap needs
+    const int32_t* btab; // uint8 convolutions: [border pattern][OCp] summed corrections of the taps a border pixel misses (engine.cu)
     unsigned long long* trace; // debug (TB200_GEMM_TRACE): event timeline of CTA 0, see gemm_trace_report
 };
 
@@ -144,48 +146,39 @@ __device__ __forceinline__ void epilogue_unit_exact(const uint32_t (&v)[16], uin
 // uint8 flavour: v = sum x*w over in-bounds taps (raw bytes), sx = sum x.  The true accumulator is
 //   sum (x-zx)(w-zw) = v - zw*sx + corr[oc] + sum_{padding taps t} btab[t][oc]
 // with corr[oc] = -zx*sum_k w + taps*Cin*zx*zw (interior pixels) folded into the per-channel constants.
-// border pixel: sum of the per-tap corrections of the taps that fell into the padding, for one channel (rare rows; a call, so
-// that the hot path carries neither the loop nor an addressable accumulator array)
-__device__ __noinline__ int32_t u8_border_correction(uint64_t pad_mask, const int32_t* __restrict__ btab, int taps, int ocp, int oc)
-{
-    int32_t c = 0;
-    if (oc < ocp)
-        for (int t = 0; t < taps; t++)
-            if ((pad_mask >> t) & 1ull) c += __ldg(btab + (size_t)t * ocp + oc);
-    return c;
-}
+// uint8 flavour: v = sum x*w over in-bounds taps (raw bytes), sx = sum x.  The true accumulator is
+//   sum (x-zx)(w-zw) = v - zw*sx + corr[oc] + sum_{padding taps t} btab[t][oc]
+// with corr[oc] = -zx*sum_k w + taps*Cin*zx*zw (interior pixels).  The per-channel constants are in the int8 layout
+// { M[2k], M[2k+1], y[2k], y[2k+1] } with y = corr + bias (an integer), so the fast path IS the int8 one on a' = v + rowc + y:
+// t = fl((float)a' * M), exact up to the tie guard under the bound engine.cu proves per layer (|bias*M| <= 250).
 
-template <bool EXACT>
-__device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_t sx, uint64_t pad_mask, const GemmArgs& g, uint32_t par_addr,
+template <bool EXACT, bool BORDER>
+__device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], uint32_t pad_mask_in, const GemmArgs& g, uint32_t par_addr,
                                                  uint32_t dst_addr, int oc0, const EpiParams& e)
 {
-    const int32_t rowc = -e.w_zero * sx;
+    constexpr int32_t rowc = 0; // (the zw * sum(x) term is formed by the second MMA now, see GemmArgs::cplane)
+    const uint32_t pad_mask = BORDER ? pad_mask_in : 0u; // BORDER == false (1x1 / FC, unpadded convs): the correction code compiles away
     uint32_t w[4];
     if (!EXACT)
     {
-        // Packed form (common.cuh requant_fast8_u8), eight channels at a time so that the live set stays below the 96-register
-        // cap of this 18-warp kernel: true accumulator = v + rowc + corr[oc] (one IADD3 per element), then the float chain on the
-        // FMA pipe as FMUL2 / FADD2 pairs, clip + zero point + saturation as one DPX op per pair.
         float gw[4];
 #pragma unroll
         for (int h = 0; h < 2; h++)
         {
-            int32_t a8[8];
-            float b8[8];
+            float4 p[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                const float4 p = lds_f4(par_addr + h * 64 + k * 16); // (bias term, corr) of channels 2k, 2k+1 of this half
-                a8[2 * k] = (int32_t)v[h * 8 + 2 * k] + rowc + __float_as_int(p.y);
-                a8[2 * k + 1] = (int32_t)v[h * 8 + 2 * k + 1] + rowc + __float_as_int(p.w);
-                b8[2 * k] = p.x, b8[2 * k + 1] = p.z;
-            }
+            for (int k = 0; k < 4; k++) p[k] = lds_f4(par_addr + h * 64 + k * 16);
+            int32_t a8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) a8[k] = (int32_t)v[h * 8 + k] + rowc; // (+ y inside requant_fast8_i8<false>: one IADD3)
             if (pad_mask)
             {
-#pragma unroll
-                for (int k = 0; k < 8; k++) a8[k] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + h * 8 + k);
+                // border row: the summed corrections of its missing taps, one 16-byte load per four channels
+                const int4* pt = reinterpret_cast<const int4*>(g.btab + (size_t)pad_mask * g.ocp + oc0 + h * 8);
+                const int4 c0 = __ldg(pt), c1 = __ldg(pt + 1);
+                a8[0] += c0.x, a8[1] += c0.y, a8[2] += c0.z, a8[3] += c0.w, a8[4] += c1.x, a8[5] += c1.y, a8[6] += c1.z, a8[7] += c1.w;
             }
-            requant_fast8_u8(a8, b8, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
+            requant_fast8_i8<false>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
         }
         if (e.q_byte_add)
         {
@@ -194,25 +187,21 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
         }
         if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
         {
-            // rare (2.4e-4 of the elements): exact recomputation of the guarded words from the raw accumulators
+            // rare (2.4e-4 of the elements): the guarded words again with the literal reference arithmetic, which wants the true
+            // accumulator WITHOUT the bias (requant() adds it in the float domain like the reference)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (gw[j] > 0.5f - TB200_TIE_EPS)
                 {
-                    int32_t a4[4];
 #pragma unroll
                     for (int t = 0; t < 4; t++)
                     {
-                        const float2 pp = lds_f2(par_addr + (j * 4 + t) * 8);
-                        a4[t] = (int32_t)v[j * 4 + t] + rowc + __float_as_int(pp.y);
+                        const int oc = oc0 + j * 4 + t;
+                        const float4 pp = lds_f4(par_addr + ((j * 4 + t) >> 1) * 16);
+                        int32_t a = (int32_t)v[j * 4 + t] + rowc + __float_as_int((t & 1) ? pp.w : pp.z);
+                        if (pad_mask && oc < g.ocp) a += __ldg(g.btab + (size_t)pad_mask * g.ocp + oc);
+                        if (oc < g.oc) w[j] = requant_fix_byte(w[j], t, a - (e.has_bias ? __ldg(e.bias + oc) : 0), oc, e);
                     }
-                    if (pad_mask)
-                    {
-#pragma unroll
-                        for (int t = 0; t < 4; t++) a4[t] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + j * 4 + t);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++) w[j] = requant_fix_byte(w[j], t, a4[t], oc0 + j * 4 + t, e);
                 }
         }
         if (oc0 + 16 > g.oc)
@@ -225,31 +214,26 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
     }
     else
     {
-        int32_t a[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) a[k] = (int32_t)v[k] + rowc;
-        if (pad_mask)
-        {
-#pragma unroll
-            for (int k = 0; k < 16; k++) a[k] += u8_border_correction(pad_mask, g.btab, g.taps, g.ocp, oc0 + k);
-        }
 #pragma unroll
         for (int k = 0; k < 16; k++)
         {
             if ((k & 3) == 0) w[k >> 2] = 0;
-            if (oc0 + k < g.oc)
+            const int oc = oc0 + k;
+            if (oc < g.oc)
             {
                 const float4 pp = lds_f4(par_addr + (k >> 1) * 16);
-                const int32_t corr = __float_as_int((k & 1) ? pp.w : pp.y);
-                w[k >> 2] |= ((uint32_t)requant(a[k] + corr, oc0 + k, e) & 0xffu) << (8 * (k & 3));
+                int32_t a = (int32_t)v[k] + rowc + __float_as_int((k & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + oc) : 0);
+                if (pad_mask) a += __ldg(g.btab + (size_t)pad_mask * g.ocp + oc);
+                w[k >> 2] |= ((uint32_t)requant(a, oc, e) & 0xffu) << (8 * (k & 3));
             }
         }
     }
     sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
 
-// taps of output pixel (oh, ow) that fall outside the image (bit t = kh*kw_n + kw)
-__device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int r)
+// border pattern of output pixel r of m-tile mt (0 = every tap inside the image): how many rows / columns of the filter window are
+// cut at the top (a), bottom (b), left (c), right (d); index into the table engine.cu builds
+__device__ __forceinline__ uint32_t padding_taps(const GemmArgs& g, int mt, int r)
 {
     if (!g.conv || g.taps == 1 && g.pad_h == 0 && g.pad_w == 0) return 0;
     int n0, oh0, ow0;
@@ -258,19 +242,18 @@ __device__ __forceinline__ uint64_t padding_taps(const GemmArgs& g, int mt, int 
     const int n = (int)(((uint32_t)t * g.bh_rcp) >> 16), h = t - n * g.bh;
     const int iy0 = (oh0 + h) * g.cstride - g.pad_h, ix0 = (ow0 + w) * g.cstride - g.pad_w;
     const int khn = g.taps / g.kw_n;
-    if (iy0 >= 0 && ix0 >= 0 && iy0 + khn <= g.in_h && ix0 + g.kw_n <= g.in_w) return 0; // interior
-    uint64_t m = 0;
-    for (int kh = 0; kh < khn; kh++)
-        for (int kw = 0; kw < g.kw_n; kw++)
-            if (iy0 + kh < 0 || iy0 + kh >= g.in_h || ix0 + kw < 0 || ix0 + kw >= g.in_w) m |= 1ull << (kh * g.kw_n + kw);
-    return m;
+    int a = -iy0, b = iy0 + khn - g.in_h, c = -ix0, d = ix0 + g.kw_n - g.in_w;
+    a = a < 0 ? 0 : a, b = b < 0 ? 0 : (b > khn ? khn : b), c = c < 0 ? 0 : c, d = d < 0 ? 0 : (d > g.kw_n ? g.kw_n : d);
+    // (a <= pad_h and c <= pad_w by construction; rows of the tile beyond the output map are clipped by the store anyway)
+    a = a > g.pad_h ? g.pad_h : a, c = c > g.pad_w ? g.pad_w : c;
+    return (uint32_t)(((a * (khn + 1) + b) * (g.pad_w + 1) + c) * (g.kw_n + 1) + d);
 }
 
 // MODE: 0 fast epilogue, 1 fast epilogue with the bias folded into the FMA (int8 only), 2 exact epilogue.
 // CS: 16-column chunks per store group (1, 2, 4 or 8).  Compile-time so that each kernel carries exactly one epilogue body.
 // CS == 8: a group is 32 rows x 128 bytes filled by a PAIR of warps (64 bytes each) and stored by one of them: the TMA
 // unit's cost is per row (~4 cycles for anything up to 128 bytes), so 128-byte rows halve the store side's share of it.
-template <bool U8, int MODE, int CS>
+template <bool U8, int MODE, int CS, bool BORDER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out_tail,
@@ -286,7 +269,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint8_t* b_region = smem + (size_t)g.stages * stage_bytes; // resident-B mode: [k_blocks][b_al]
     constexpr uint32_t buf_bytes = 512u * CS; // 32 rows x 16*CS bytes
     constexpr int WCH = CS == 8 ? 4 : CS;     // chunks one warp requantises per group
-    uint8_t* stg = b_region + (g.b_res ? (size_t)g.k_blocks * b_al : 0);
+    uint8_t* cst = b_region + (g.b_res ? (size_t)g.k_blocks * b_al : 0); // uint8: the constant B tile (b_al bytes when cplane != 0)
+    uint8_t* stg = cst + (g.cplane ? b_al : 0u);
     const uint32_t stg_base = smem_u32(stg);
     GemmSmemCtl* ctl = reinterpret_cast<GemmSmemCtl*>(stg + (size_t)(CS == 8 ? EPI_WARPS / 2 : EPI_WARPS) * 2 * buf_bytes);
     const uint32_t par_base = smem_u32(ctl) + (uint32_t)sizeof(GemmSmemCtl); // [par channels] x 8 bytes (see FastPar4)
@@ -310,6 +294,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1), mbar_init(&ctl->tmem_empty[s], g.teams ? EPI_WARPS / 2 : EPI_WARPS);
         mbar_init(&ctl->b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (g.cplane)
+    {
+        // every byte the same, so no swizzle to respect; read by the MMAs through the async proxy
+        const uint32_t c4 = (uint32_t)(g.cplane & 0xff) * 0x01010101u;
+        for (uint32_t i = threadIdx.x * 16u; i < b_al; i += GEMM_THREADS * 16u) sts_u4(smem_u32(cst) + i, c4, c4, c4, c4);
+        fence_proxy_async_smem();
     }
     if (warp == 0)
     {
@@ -410,10 +401,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                         const uint32_t sb = g.b_res ? smem_u32(b_region) + (uint32_t)kb * b_al : sa + a_bytes;
                         const uint64_t da = make_smem_desc(sa, g.swizzle), db = make_smem_desc(sb, g.swizzle);
+                        const uint64_t dc = make_smem_desc(smem_u32(cst), g.swizzle);
                         for (int k = 0; k < g.block_k / 32; k++)
                         {
                             // advance 32 bytes (one UMMA_K of int8) inside the swizzled row: +2 in 16-byte units
                             umma_i8(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), g.idesc, (kb | k) ? 1u : 0u);
+                            if (g.cplane) umma_i8(tmem_d, da + (uint64_t)(k * 2), dc, g.idesc, 1u); // + x * (128 - zw)
                         }
                         tcgen05_commit(&ctl->empty[stage]); // smem stage reusable once these MMAs have read it
                         tlog(1, 0);
@@ -496,10 +489,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (qrows > 0)
             {
                 // groups of this warp: flattened index u = i * ngroups + grp, u = sub, sub + 4, ...
+                // (uint8: a packed FMUL2 / FADD2 epilogue -- 16 columns with spills, and 8 columns per tcgen05.ld without -- was measured
+                //  SLOWER than the scalar unit in this kernel: ResNet-50 uint8 b=512 1x1 layers 8.5 / 8.7 ms vs 7.0 ms)
                 uint32_t v0[16], v1[16];
                 int i = 0, grp = gfirst;
                 while (grp >= ngroups) grp -= ngroups, i++;
-                if (CS > 1 && i < mtc) tmem_ld16(tbase + i * g.bnx + grp * (CS * 16) + half * 64, v0);
+                if (CS > 1 && i < mtc)
+                    tmem_ld16(tbase + i * g.bnx + grp * (CS * 16) + half * 64, reinterpret_cast<uint32_t(&)[16]>(v0));
                 while (i < mtc)
                 {
                     int i2 = i, g2 = grp + gstep; // the group after this one
@@ -509,14 +505,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     if (lane == 0 && half == 0) bulk_wait_read<1>();
                     if (CS == 8) pair_sync();
                     else __syncwarp();
-                    int32_t sx = 0;
-                    uint64_t pad = 0;
-                    if (U8)
-                    {
-                        // warp-collective TMEM load (column block_n = sum of the pixel's inputs), once per group
-                        sx = (int32_t)tmem_ld1(tbase + i * g.bnx + g.block_n);
-                        pad = padding_taps(g, mt0 + i, q * 32 + lane);
-                    }
+                    uint32_t pad = 0;
+                    if (U8 && BORDER) pad = padding_taps(g, mt0 + i, q * 32 + lane);
                     const uint32_t tg = tbase + i * g.bnx + grp * (CS * 16) + half * 64;
                     const int cg0 = grp * (CS * 16); // first column of the group inside the N tile
                     const uint32_t sdst = buf + row_off;
@@ -524,15 +514,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     {
                         const int c = cg0 + half * 64 + k * 16;
                         const uint32_t dst = sdst + (((uint32_t)(half * 4 + k) << 4) ^ xl);
-                        if (U8) epilogue_unit_u8<MODE == 2>(v, sx, pad, g, par_s + c * 8, dst, n0 + c, e);
+                        if (U8) epilogue_unit_u8<MODE == 2, BORDER>(v, pad, g, par_s + c * 8, dst, n0 + c, e);
                         else if (MODE == 2) epilogue_unit_exact(v, dst, n0 + c, g.oc, e);
                         else epilogue_unit_fast<MODE == 1>(v, par_s + c * 8, dst, n0 + c, e);
                     };
                     if (CS == 1)
                     {
-                        tmem_ld16(tg, v0);
+                        tmem_ld16(tg, reinterpret_cast<uint32_t(&)[16]>(v0));
                         tmem_ld_wait();
-                        unit(v0, 0);
+                        unit(reinterpret_cast<const uint32_t(&)[16]>(v0), 0);
                     }
                     else
                     {
@@ -542,9 +532,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             tmem_ld_wait();
                             TLOG_E(3);
                             // the next chunk's accumulators are in flight while this one is requantised
-                            if (k + 1 < WCH) tmem_ld16(tg + (k + 1) * 16, (k & 1) ? v0 : v1);
-                            else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16) + half * 64, v0);
-                            unit((k & 1) ? v1 : v0, k);
+                            if (k + 1 < WCH) tmem_ld16(tg + (k + 1) * 16, reinterpret_cast<uint32_t(&)[16]>(*((k & 1) ? v0 : v1)));
+                            else if (i2 < mtc) tmem_ld16(tbase + i2 * g.bnx + g2 * (CS * 16) + half * 64, reinterpret_cast<uint32_t(&)[16]>(v0));
+                            unit(reinterpret_cast<const uint32_t(&)[16]>(*((k & 1) ? v1 : v0)), k);
                             TLOG_E(4);
                         }
                     }
@@ -1009,28 +999,64 @@ __global__ void __launch_bounds__(128) conv_gather_tc_kernel(const GatherArgs a,
             uint32_t w[4];
             if (U8)
             {
-                int32_t acc[16];
-                float bt[16];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    const float4 p01 = lds_f4(sPar + c * 8 + j * 32), p23 = lds_f4(sPar + c * 8 + j * 32 + 16);
-                    // (bias term, corr[oc]) per channel: corr = -zx*sum(w) + K*zx*zw travels in the .y lanes
-                    acc[j * 4 + 0] = (int32_t)v[j * 4 + 0] + rowc + __float_as_int(p01.y), acc[j * 4 + 1] = (int32_t)v[j * 4 + 1] + rowc + __float_as_int(p01.w);
-                    acc[j * 4 + 2] = (int32_t)v[j * 4 + 2] + rowc + __float_as_int(p23.y), acc[j * 4 + 3] = (int32_t)v[j * 4 + 3] + rowc + __float_as_int(p23.w);
-                    bt[j * 4 + 0] = p01.x, bt[j * 4 + 1] = p01.z, bt[j * 4 + 2] = p23.x, bt[j * 4 + 3] = p23.z;
-                }
+                // the int8 form (engine.cu: constants { M, M, y, y } with y = corr[oc] + bias[oc]): a' = v - zw*sum(x) + y, t = fl(a' * M)
                 if (MODE == 2)
                 {
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
                         if ((k & 3) == 0) w[k >> 2] = 0;
-                        if (c + k < a.oc) w[k >> 2] |= ((uint32_t)requant(acc[k], c + k, e) & 0xffu) << (8 * (k & 3));
+                        if (c + k < a.oc)
+                        {
+                            const float4 pp = lds_f4(sPar + c * 8 + (k >> 1) * 16);
+                            const int32_t acc = (int32_t)v[k] + rowc + __float_as_int((k & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + c + k) : 0);
+                            w[k >> 2] |= ((uint32_t)requant(acc, c + k, e) & 0xffu) << (8 * (k & 3));
+                        }
                     }
                 }
                 else
-                    requant_unit16_u8(acc, bt, c, a.oc, e, w);
+                {
+                    float gw[4];
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                    {
+                        float4 p[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) p[k] = lds_f4(sPar + c * 8 + h * 64 + k * 16);
+                        int32_t a8[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) a8[k] = (int32_t)v[h * 8 + k] + rowc;
+                        requant_fast8_i8<false>(a8, p, e, w[2 * h], w[2 * h + 1], gw[2 * h], gw[2 * h + 1]);
+                    }
+                    if (e.q_byte_add)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) w[j] = requant_byte_fix(w[j], e);
+                    }
+                    if (fmaxf(fmaxf(gw[0], gw[1]), fmaxf(gw[2], gw[3])) > 0.5f - TB200_TIE_EPS)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (gw[j] > 0.5f - TB200_TIE_EPS)
+                            {
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                {
+                                    const int oc = c + j * 4 + t;
+                                    const float4 pp = lds_f4(sPar + c * 8 + ((j * 4 + t) >> 1) * 16);
+                                    const int32_t acc = (int32_t)v[j * 4 + t] + rowc + __float_as_int((t & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + oc) : 0);
+                                    if (oc < a.oc) w[j] = requant_fix_byte(w[j], t, acc, oc, e);
+                                }
+                            }
+                    }
+                    if (c + 16 > a.oc)
+                    {
+                        // pad lanes of uint8 tensors hold 0, not the zero point
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if (c + k >= a.oc) w[k >> 2] &= ~(0xffu << (8 * (k & 3)));
+                    }
+                }
             }
             else if (MODE == 2)
             {
@@ -1300,8 +1326,8 @@ static int encode_2d(void* tmap, const void* base, uint64_t inner, uint64_t rows
 
 int gemm_block_n(int ocp, int u8)
 {
-    if (!u8) return ocp <= 256 ? ocp : 128;
-    return ocp <= 240 ? ocp : 112; // +16 rows for the ones-row keeps the UMMA N at <= 256 / 128
+    (void)u8; // uint8 tiles are the int8 ones: the zero points are folded by a second MMA, not by an extra accumulator column
+    return ocp <= 256 ? ocp : 128;
 }
 
 // Store-group width and output tensor maps.  A group is 32 rows x 16*cs channels; cs is the largest of 4 / 2 / 1 that
@@ -1355,7 +1381,7 @@ static int epilogue_smem_bytes(const GemmPlan* p)
 static int plan_ring(GemmPlan* p)
 {
     const int a_bytes = BLOCK_M * p->block_k, b_al = (p->bnx * p->block_k + 1023) & ~1023;
-    const int budget = 224 * 1024 - epilogue_smem_bytes(p);
+    const int budget = 224 * 1024 - epilogue_smem_bytes(p) - (p->cplane ? b_al : 0);
     p->b_res = ((long long)p->k_blocks * b_al <= B_RESIDENT_MAX && !getenv("TB200_GEMM_NO_BRES")) ? 1 : 0;
     int stages = p->b_res ? (budget - p->k_blocks * b_al) / a_bytes : budget / (a_bytes + b_al);
     if (p->b_res && stages < 3) p->b_res = 0, stages = budget / (a_bytes + b_al);
@@ -1374,9 +1400,11 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
     p->block_k = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     p->swizzle = p->block_k;
     p->k_blocks = (k + p->block_k - 1) / p->block_k;
-    p->u8 = u8;
+    p->u8 = u8 != 0; // u8 = 1 + weight zero point for uint8 layers
+    p->b_signed = !p->u8 || u8 != 1;
+    p->cplane = (p->u8 && u8 != 1) ? 128 - (u8 - 1) : 0;
     p->block_n = gemm_block_n(ocp, u8);
-    p->bnx = p->block_n + (u8 ? 16 : 0);
+    p->bnx = p->block_n;
     p->taps = 1;
     p->n_tiles = (ocp + p->block_n - 1) / p->block_n;
     p->m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
@@ -1432,9 +1460,11 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out,
     p->cblocks = (s.cp + p->block_k - 1) / p->block_k;
     p->k_blocks = taps * p->cblocks;
     p->k = taps * s.cp;
-    p->u8 = u8;
+    p->u8 = u8 != 0; // u8 = 1 + weight zero point for uint8 layers
+    p->b_signed = !p->u8 || u8 != 1;
+    p->cplane = (p->u8 && u8 != 1) ? 128 - (u8 - 1) : 0;
     p->block_n = gemm_block_n(s.ocp, u8);
-    p->bnx = p->block_n + (u8 ? 16 : 0);
+    p->bnx = p->block_n;
     p->taps = taps, p->in_h = s.h, p->in_w = s.w;
     if (taps > 64) return TB200_ERR_UNSUPPORTED;
     p->n_tiles = (s.ocp + p->block_n - 1) / p->block_n;
@@ -1568,13 +1598,13 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     g.conv = p.conv, g.cblocks = p.cblocks, g.kw_n = p.kw_n, g.pad_h = p.pad_h, g.pad_w = p.pad_w, g.cstride = p.cstride, g.cp = p.cp;
     g.bw = p.bw, g.bh = p.bh, g.bn = p.bn, g.tiles_w = p.tiles_w, g.tiles_h = p.tiles_h, g.oh = p.oh, g.ow = p.ow, g.nimg = p.nimg;
     g.a_tx_bytes = p.a_tx_bytes;
-    g.u8 = p.u8, g.bnx = p.bnx, g.taps = p.taps, g.in_h = p.in_h, g.in_w = p.in_w, g.btab = btab;
+    g.u8 = p.u8, g.bnx = p.bnx, g.taps = p.taps, g.in_h = p.in_h, g.in_w = p.in_w, g.btab = btab, g.b_signed = p.b_signed, g.cplane = p.cplane;
     g.mt = p.mt;
     g.num_super = (int)(((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles);
     g.bw_rcp = p.conv ? (65536u + (uint32_t)p.bw - 1) / (uint32_t)p.bw : 0;
     g.bh_rcp = p.conv ? (65536u + (uint32_t)p.bh - 1) / (uint32_t)p.bh : 0;
     g.block_k = p.block_k, g.stages = p.stages, g.swizzle = p.swizzle, g.oc = p.oc, g.ocp = p.ocp;
-    g.idesc = make_idesc_i8(p.bnx, !p.u8, !p.u8);
+    g.idesc = make_idesc_i8(p.bnx, !p.u8, p.b_signed != 0);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * p.mt * p.bnx)) cols <<= 1;
     g.tmem_cols = cols;
@@ -1585,7 +1615,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     g.b_res = p.b_res;
     static const int teams_env = getenv("TB200_GEMM_TEAMS") ? atoi(getenv("TB200_GEMM_TEAMS")) : 0;
     g.teams = (teams_env && p.cs != 8 && p.n_tiles * p.block_n <= PAR_MAX) ? 1 : 0;
-    const size_t smem = (size_t)p.stages * (a_bytes + (p.b_res ? 0 : b_bytes)) + (p.b_res ? (size_t)p.k_blocks * b_bytes : 0) +
+    const size_t smem = (size_t)p.stages * (a_bytes + (p.b_res ? 0 : b_bytes)) + (p.b_res ? (size_t)p.k_blocks * b_bytes : 0) + (p.cplane ? b_bytes : 0) +
                         (size_t)EPI_WARPS * 2 * 512 * (p.cs == 8 ? 4 : p.cs) + sizeof(GemmSmemCtl) +
                         (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
     static const bool trace_on = getenv("TB200_GEMM_TRACE") != nullptr;
@@ -1606,26 +1636,30 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     memcpy(&tt, p.tmap_out_tail, sizeof tt);
     const int mode = !e.fast_ok ? 2 : ((!p.u8 && e.fuse_bias) ? 1 : 0);
     cudaError_t err = cudaErrorInvalidValue;
-#define TB200_GEMM_CASE(U, MD, C)                                                                                              \
-    if ((p.u8 != 0) == U && mode == MD && p.cs == C)                                                                           \
+    // uint8 border corrections only exist for convolutions with taps that can fall into the padding
+    const bool border = p.u8 && p.conv && !(p.taps == 1 && p.pad_h == 0 && p.pad_w == 0);
+#define TB200_GEMM_CASE(U, MD, C, B)                                                                                           \
+    if ((p.u8 != 0) == U && mode == MD && p.cs == C && border == B)                                                            \
     {                                                                                                                          \
         static bool attr = false;                                                                                              \
         if (!attr)                                                                                                             \
         {                                                                                                                      \
-            err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             if (err != cudaSuccess) return err;                                                                                \
             attr = true;                                                                                                       \
         }                                                                                                                      \
-        gemm_i8_tcgen05_kernel<U, MD, C><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, to, tt, g, e);                              \
+        gemm_i8_tcgen05_kernel<U, MD, C, B><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, to, tt, g, e);                           \
         if (trace_on) gemm_trace_report(p, g, grid, st);                                                                       \
         return cudaGetLastError();                                                                                             \
     }
-#define TB200_GEMM_CS(U, MD) TB200_GEMM_CASE(U, MD, 1) TB200_GEMM_CASE(U, MD, 2) TB200_GEMM_CASE(U, MD, 4) TB200_GEMM_CASE(U, MD, 8)
-    TB200_GEMM_CS(false, 0)
-    TB200_GEMM_CS(false, 1)
-    TB200_GEMM_CS(false, 2)
-    TB200_GEMM_CS(true, 0)
-    TB200_GEMM_CS(true, 2)
+#define TB200_GEMM_CS(U, MD, B) TB200_GEMM_CASE(U, MD, 1, B) TB200_GEMM_CASE(U, MD, 2, B) TB200_GEMM_CASE(U, MD, 4, B) TB200_GEMM_CASE(U, MD, 8, B)
+    TB200_GEMM_CS(false, 0, false)
+    TB200_GEMM_CS(false, 1, false)
+    TB200_GEMM_CS(false, 2, false)
+    TB200_GEMM_CS(true, 0, false)
+    TB200_GEMM_CS(true, 2, false)
+    TB200_GEMM_CS(true, 0, true)
+    TB200_GEMM_CS(true, 2, true)
 #undef TB200_GEMM_CS
 #undef TB200_GEMM_CASE
     return err;

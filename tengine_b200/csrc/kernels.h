@@ -61,6 +61,30 @@ struct DwPlan
 int dw_plan_create(DwPlan* plan, const void* in, const ConvShape& s, const EpiParams& e);
 cudaError_t launch_conv_dw_tma(const DwPlan& plan, const void* w, void* out, const ConvShape& s, const EpiParams& e, cudaStream_t st);
 
+// ---- fp32 members of the path (conv_fp32.cu): Winograd F(4x4,3x3) and depthwise 3x3 on NCHW fp32 ---------------
+size_t wino43_workspace_bytes(int n, int c, int oc, int oh, int ow);
+cudaError_t launch_conv_winograd43_f32(const float* in, const float* w, const float* bias, float* out, int n, int c, int h, int wd, int oc, int oh, int ow, int ph,
+                                       int pw, int activation, float* ws, cudaStream_t st);
+cudaError_t launch_conv_dw3x3_f32(const float* in, const float* w, const float* bias, float* out, int n, int c, int h, int wd, int oh, int ow, int stride, int ph,
+                                  int pw, int activation, cudaStream_t st);
+
+// ---- detection post-processing (yolo_detect.cu) ----------------------------------------------------------------
+struct YoloCand
+{
+    float x, y, w, h, prob;
+    int label;
+    unsigned key; // position in the reference's proposal list (head order, then h, w, anchor)
+};
+struct YoloDet
+{
+    float x, y, w, h, prob;
+    int label;
+};
+cudaError_t launch_yolo_decode(const void* tensor, int cp, int h, int w, int n_img, int anchors_n, int classes, const float* sig, const double* ex, float stride,
+                               const float* anchors6, float thr, YoloCand* cand, int* count, int max_cand, unsigned key_base, bool is_u8, cudaStream_t st);
+cudaError_t launch_yolo_nms(const YoloCand* cand, const int* count, int n_img, int max_cand, float nms_thr, YoloCand* sorted, YoloDet* out, int max_out,
+                            int* out_count, cudaStream_t st);
+
 // ---- small-Cin convolutions with a TMA-staged input window (conv_window.cu) -----------------------------------
 struct WindowPlan
 {
@@ -89,7 +113,8 @@ struct GemmPlan
     // conv mode (implicit GEMM over a 4-D tensor map)
     int conv, cblocks, kw_n, pad_h, pad_w, cstride, cp, bw, bh, bn, tiles_w, tiles_h, oh, ow, nimg;
     unsigned a_tx_bytes;
-    int u8, bnx, taps, in_h, in_w; // uint8: B tiles carry 16 extra rows (ones-row -> per-pixel sum of x)
+    int u8, bnx, taps, in_h, in_w; // uint8: unsigned A operand
+    int b_signed, cplane;          // uint8: B holds w - 128 as int8, a constant tile of value 128 - zw folds the rest (gemm_tcgen05.cu)
     long long m_tiles;
     int swizzle; // 32 / 64 / 128
     int cs, ngroups, rows_valid, out_mode; // epilogue store groups, see gemm_tcgen05.cu plan_epilogue

@@ -36,6 +36,8 @@ extern "C" {
 #include "operator/prototype/softmax_param.h"
 }
 
+#include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -202,7 +204,6 @@ int conv_recipe(const struct conv_param* p, const struct tensor* in, const struc
 int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options)
 {
     (void)dev;
-    if (ensure_context(options) != 0) return -1; // options: NULL for apps that never call set_context_device (scheduler.c:49-57)
     struct graph* ir_graph = subgraph->graph;
 
     std::map<uint16_t, int> tmap; // ir tensor id -> index in the ABI tensor table
@@ -340,6 +341,43 @@ int b200_dev_prerun(struct device* dev, struct subgraph* subgraph, void* options
     {
         bg->outputs.push_back(subgraph->output_tensor_list[i]);
         out_ids.push_back(tensor_id(subgraph->output_tensor_list[i]));
+    }
+    if (const char* dump = getenv("TG_B200_DUMP_DESC"))
+    {
+        // debug: the descriptor tables exactly as they go to tb200_graph_prerun (text; constants as FNV-1a hashes)
+        if (FILE* f = fopen(dump, "a"))
+        {
+            fprintf(f, "# subgraph %d: %d nodes, %d inputs, %d outputs\n", subgraph->index, subgraph->node_num, subgraph->input_num, subgraph->output_num);
+            auto fnv = [](const void* p, size_t n) {
+                uint64_t h = 1469598103934665603ull;
+                for (size_t i = 0; i < n; i++) h = (h ^ ((const uint8_t*)p)[i]) * 1099511628211ull;
+                return (unsigned long long)h;
+            };
+            for (size_t i = 0; i < tensors.size(); i++)
+                fprintf(f, "T%zu dt%d [%d %d %d %d] scale %.9g zp %d\n", i, tensors[i].data_type, tensors[i].dims[0], tensors[i].dims[1], tensors[i].dims[2],
+                        tensors[i].dims[3], tensors[i].scale, tensors[i].zero_point);
+            for (size_t i = 0; i < layers.size(); i++)
+            {
+                const tb200_layer_desc& L = layers[i];
+                const tb200_tensor_desc& to = tensors[L.output];
+                const tb200_tensor_desc& ti = tensors[L.inputs[0]];
+                size_t wn = 0;
+                if (L.op == TB200_OP_CONV) wn = (size_t)to.dims[1] * (ti.dims[1] / L.group) * L.kernel_h * L.kernel_w;
+                if (L.op == TB200_OP_FC) wn = (size_t)to.dims[1] * ti.dims[1] * ti.dims[2] * ti.dims[3];
+                fprintf(f, "L%zu op%d in[%d %d %d %d]/%d out%d k%dx%d s%d,%d p%d,%d,%d,%d d%d,%d g%d act%d rec%d pool%d,%d,%d slope%.9g elt%d axis%d up%d wz%d bs%.9g w%llx b%llx ws%llx\n",
+                        i, L.op, L.inputs[0], L.inputs[1], L.inputs[2], L.inputs[3], L.num_inputs, L.output, L.kernel_h, L.kernel_w, L.stride_h, L.stride_w, L.pad_h0,
+                        L.pad_h1, L.pad_w0, L.pad_w1, L.dilation_h, L.dilation_w, L.group, L.activation, L.recipe, L.pool_method, L.pool_global, L.caffe_flavor,
+                        L.negative_slope, L.elt_type, L.axis, L.up_scale, L.weight_zero, L.bias_scale, wn ? fnv(L.weight, wn) : 0ull,
+                        (wn && L.bias) ? fnv(L.bias, (size_t)to.dims[1] * 4) : 0ull,
+                        wn ? fnv(L.weight_scales, ti.data_type == TB200_DT_UINT8 ? 4 : (size_t)to.dims[1] * 4) : 0ull);
+            }
+            fclose(f);
+        }
+    }
+    if (ensure_context(options) != 0) // options: NULL for apps that never call set_context_device (scheduler.c:49-57)
+    {
+        delete bg;
+        return -1;
     }
     int flags = TB200_PRERUN_DEFAULT;
     if (getenv("TG_B200_NO_TENSORCORE")) flags |= TB200_PRERUN_NO_TENSORCORE;

@@ -72,6 +72,8 @@ def lib():
         L.tb200_graph_shard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tb200_graph_arena_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tb200_graph_broadcast_weights.argtypes = [C.c_void_p]
+        L.tb200_pack_cache_dir.argtypes = [C.c_char_p]
+        L.tb200_graph_pack_cache_state.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -79,6 +81,11 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise TB200Error(rc, lib().tb200_last_error().decode(errors="replace"))
+
+
+def set_pack_cache_dir(path):
+    """Directory of the packed-weight cache (None disables); see include/tengine_b200.h tb200_pack_cache_dir."""
+    lib().tb200_pack_cache_dir(path.encode() if path else None)
 
 
 def device_count():
@@ -213,6 +220,33 @@ class Graph:
         a, u, w = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _check(lib().tb200_graph_arena_bytes(self.h, C.byref(a), C.byref(u), C.byref(w)))
         return a.value, u.value, w.value
+
+    def yolo_detect(self, heads, num_classes=80, prob_threshold=0.4, nms_threshold=0.25, max_per_image=256, max_candidates=0):
+        """Region decode + NMS on the device from the graph's output tensors of the last run (tb200_graph_yolo_detect).
+        heads: [(graph output index, stride, six anchor values)] in proposal order.  Returns per image a list of
+        (x, y, w, h, prob, label)."""
+        p = abi.YoloParams()
+        p.num_heads = len(heads)
+        for i, (oi, stride, anchors) in enumerate(heads):
+            p.heads[i].output_index, p.heads[i].stride = int(oi), int(stride)
+            for k in range(6):
+                p.heads[i].anchors[k] = float(anchors[k])
+        p.num_classes, p.prob_threshold, p.nms_threshold, p.max_candidates = int(num_classes), float(prob_threshold), float(nms_threshold), int(max_candidates)
+        n = self.gdef.dims(self.gdef.outputs[0])[0]
+        out = (abi.Detection * (n * max_per_image))()
+        counts = (C.c_int32 * n)()
+        lib().tb200_graph_yolo_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _check(lib().tb200_graph_yolo_detect(self.h, C.byref(p), out, int(max_per_image), counts))
+        res = []
+        for i in range(n):
+            if counts[i] < 0:
+                raise TB200Error(abi.ERR_INVALID, f"image {i}: {-counts[i]} boxes / candidates do not fit")
+            res.append([(d.x, d.y, d.w, d.h, d.prob, d.label) for d in out[i * max_per_image:i * max_per_image + counts[i]]])
+        return res
+
+    def pack_cache_state(self):
+        """0: no cache directory, 1: packed and written to the cache, 2: arena image read from the cache."""
+        return lib().tb200_graph_pack_cache_state(self.h)
 
     def close(self):
         if self.h:

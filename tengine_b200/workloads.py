@@ -325,3 +325,48 @@ def yolov3_tiny(data_type=abi.DT_UINT8, batch=1, res=416, seed=1234, width=1.0, 
     o26 = b.identity(b.conv(y, head, 1, activation=-1))
     o13 = b.identity(b.conv(big, head, 1, activation=-1))
     return b.finish([o26, o13]), b
+
+
+def yolov5s(data_type=abi.DT_INT8, batch=1, res=640, seed=1234, width=1.0, head=255):
+    """YOLOv5s (v5.0 graph: Focus, C3 x {1,3,3,1}, SPP 5/9/13, PANet head, three 1x1 detection convs) in the form the reference
+    pipeline runs it (tools/optimize/yolov5s-opt.py:114-156 cuts the Focus slicing and the post-processing out of the graph, so
+    the network input is the app-sliced [N, 12, res/2, res/2] tensor -- examples/tm_yolov5s.cpp -- and the outputs are the three
+    raw head tensors).  Activation: the script rewrites SiLU to HardSwish, which the reference CPU device only has for fp32 /
+    uint8 (hardswish_ref.c:59-66); an int8 model therefore keeps SiLU as Sigmoid + Eltwise-PROD (sigmoid_ref.c:84,
+    eltwise_ref.c:589).  BatchNorm is folded into the convolutions' bias as in every reference tmfile."""
+    b = QuantBuilder(data_type, batch, 12, res // 2, res // 2, seed, inplace=True)
+    ch = lambda c: max(8, int(c * width))
+
+    def act(x):
+        return b.hardswish(x) if b.u8 else b.mul(x, b.sigmoid(x))
+
+    def conv(x, oc, k=1, s=1):
+        return act(b.conv(x, oc, k, stride=s, pad=k // 2, activation=-1))
+
+    def c3(x, oc, n, shortcut=True):
+        c_ = oc // 2
+        y = conv(x, c_, 1)
+        for _ in range(n):
+            z = conv(conv(y, c_, 1), c_, 3)
+            y = b.add(y, z) if shortcut else z
+        return conv(b.concat([y, conv(x, c_, 1)]), oc, 1)
+
+    x = conv(b.input, ch(32), 3)                    # Focus convolution
+    x = conv(x, ch(64), 3, 2)
+    x = c3(x, ch(64), 1)
+    x = conv(x, ch(128), 3, 2)
+    p3 = c3(x, ch(128), 3)
+    x = conv(p3, ch(256), 3, 2)
+    p4 = c3(x, ch(256), 3)
+    x = conv(p4, ch(512), 3, 2)
+    y = conv(x, ch(256), 1)                          # SPP
+    x = conv(b.concat([y] + [b.pool(y, abi.POOL_MAX, k, 1, k // 2) for k in (5, 9, 13)]), ch(512), 1)
+    x = c3(x, ch(512), 1, shortcut=False)
+    h10 = conv(x, ch(256), 1)
+    x = c3(b.concat([b.upsample(h10, 2), p4]), ch(256), 1, shortcut=False)
+    h14 = conv(x, ch(128), 1)
+    o17 = c3(b.concat([b.upsample(h14, 2), p3]), ch(128), 1, shortcut=False)
+    o20 = c3(b.concat([conv(o17, ch(128), 3, 2), h14]), ch(256), 1, shortcut=False)
+    o23 = c3(b.concat([conv(o20, ch(256), 3, 2), h10]), ch(512), 1, shortcut=False)
+    outs = [b.conv(o, head, 1, activation=-1) for o in (o17, o20, o23)]
+    return b.finish(outs), b

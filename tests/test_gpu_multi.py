@@ -5,6 +5,8 @@ afterwards.  Checked: every shard's bytes (rank > 0 included) equal the oracle's
 On a box with one GPU the group lists device 0 twice: NCCL refuses duplicate devices, so the arena travels by
 cudaMemcpyPeerAsync, but everything else -- the NO_WEIGHTS prerun of shards > 0, slicing of the caller's buffers, per-shard
 streams, the merge of the outputs -- is the code that runs on 2/4/8 GPUs.  With >= 2 GPUs the NCCL path itself is tested."""
+import os
+
 import numpy as np
 import pytest
 
@@ -166,3 +168,78 @@ def test_uint8_fc_bias_scale(ctx, oracle):
         got = gr.run([xin])[0]
         gr.close()
         assert np.array_equal(got, oracle.run(g, [xin], uint8_mode=0)[y])
+
+
+def test_pack_cache_round_trip(ctx, oracle, tmp_path):
+    """the packed weight arena is written under a hash of everything it depends on; a second prerun of the same
+    model reads it back (same bytes on the device, same results); a model with other weights gets another entry."""
+    import time
+
+    from tengine_b200 import runtime as rt
+
+    rt.set_pack_cache_dir(str(tmp_path))
+    try:
+        g, b = workloads.resnet50(abi.DT_UINT8, batch=2, res=64, width=0.5, classes=30, seed=9)
+        x = b.random_input(1)
+        want = oracle.run(g, [x], uint8_mode=0)[g.outputs[0]]
+        t0 = time.perf_counter()
+        gr = rt.Graph(ctx, g)
+        t_pack = time.perf_counter() - t0
+        assert gr.pack_cache_state() == 1
+        y1 = gr.run([x])[0]
+        gr.close()
+        files = sorted(os.listdir(tmp_path))
+        assert len(files) == 1 and files[0].endswith(".pack")
+        t0 = time.perf_counter()
+        gr = rt.Graph(ctx, g)
+        t_hit = time.perf_counter() - t0
+        assert gr.pack_cache_state() == 2
+        y2 = gr.run([x])[0]
+        gr.close()
+        assert np.array_equal(y1, want) and np.array_equal(y2, want)
+        g2, _ = workloads.resnet50(abi.DT_UINT8, batch=2, res=64, width=0.5, classes=30, seed=10)  # other weights
+        gr = rt.Graph(ctx, g2)
+        assert gr.pack_cache_state() == 1
+        gr.close()
+        assert len(os.listdir(tmp_path)) == 2
+        print(f"prerun with packing {t_pack * 1e3:.1f} ms, from the cache {t_hit * 1e3:.1f} ms")
+    finally:
+        rt.set_pack_cache_dir(None)
+    gr = rt.Graph(ctx, g)
+    assert gr.pack_cache_state() == 0
+    gr.close()
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_yolo_detect_on_device_equals_the_examples_post_processing(oracle, gpus):
+    """region decode + threshold + sort + NMS on the device, from the quantised head tensors in HBM, against the
+    CPU restatement of examples/tm_yolov3_tiny_uint8.cpp's post-processing (oracle/yolo_post.py) on the same bytes: the same boxes
+    in the same order, bit-identical floats."""
+    from oracle import yolo_post
+    from tengine_b200 import runtime as rt
+
+    g, b = workloads.yolov3_tiny(abi.DT_UINT8, batch=5, res=160, width=0.5, seed=8)
+    x = b.random_input(3)
+    c = rt.Context(devices=_devices(gpus)) if gpus > 1 else rt.Context(0)
+    anchors = [10, 14, 23, 27, 37, 58, 81, 82, 135, 169, 344, 319]
+    # the example's order: the stride-32 head (anchors[6:12]) first, then stride 16 (anchors[0:6]); graph outputs are (26x26, 13x13)-like
+    heads = [(1, 32, anchors[6:12]), (0, 16, anchors[0:6])]
+    try:
+        gr = rt.Graph(c, g)
+        outs = gr.run([x])
+        # low threshold: random-weight heads rarely reach the example's 0.4
+        got = gr.yolo_detect(heads, num_classes=80, prob_threshold=0.27, nms_threshold=0.25, max_per_image=512)
+        gr.close()
+    finally:
+        c.close()
+    want_raw = oracle.run(g, [x], uint8_mode=0)
+    for o, t in zip(outs, g.outputs):
+        assert np.array_equal(o, want_raw[t])
+    scales = [g.tensors[t]["scale"] for t in g.outputs]
+    zeros = [g.tensors[t]["zero_point"] for t in g.outputs]
+    want = yolo_post.detect(outs, scales, zeros, heads, 80, 0.27, 0.25)
+    assert sum(len(w) for w in want) > 20, "test vacuous: nothing passes the threshold"
+    for i, (gd, wd) in enumerate(zip(got, want)):
+        assert len(gd) == len(wd), (i, len(gd), len(wd))
+        for a, w in zip(gd, wd):
+            assert a[5] == w[5] and all(np.float32(a[k]) == np.float32(w[k]) for k in range(5)), (i, a, w)

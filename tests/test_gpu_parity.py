@@ -304,6 +304,39 @@ def test_full_size_batch_independence(ctx, oracle, net, dtype, batch):
         assert np.array_equal(o_big[:2], want[t])
 
 
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+def test_yolov5s_every_layer(ctx, oracle, dtype):
+    """C5 (YOLOv5s 640x640: conv + sigmoid*x / HardSwish, C3 blocks, SPP 5/9/13 max pools, 4-input concat, PANet head) at full
+    size, batch 2: every layer bit-exact against the oracle; then the default plan (captured graph, fused nodes, slot reuse)."""
+    from tengine_b200 import runtime as rt
+
+    g, b = workloads.yolov5s(dtype, batch=2)
+    x = b.random_input(4)
+    outs, tensors, kernels = _run_all_layers(ctx, g, x, abi.PRERUN_DEFAULT)
+    want = oracle.run(g, [x], uint8_mode=0)
+    for li, L in enumerate(g.layers):
+        assert np.array_equal(tensors[L["output"]], want[L["output"]]), f"yolov5s layer {li} {abi.OP_NAMES[L['op']]} ({kernels[li]})"
+    gr = rt.Graph(ctx, g)
+    fast = gr.run([x])
+    gr.close()
+    for o, t in zip(fast, g.outputs):
+        assert np.array_equal(o, want[t]) and len(np.unique(o)) > 50
+
+
+def test_eltwise_relu_fusion_is_used_and_exact(ctx, oracle):
+    from tengine_b200 import runtime as rt
+
+    g, b = workloads.resnet50(abi.DT_UINT8, batch=2, res=64, width=0.5, classes=30, seed=9)
+    x = b.random_input(1)
+    gr = rt.Graph(ctx, g)
+    try:
+        assert gr.layer_kernels().count("fused_into_producer") == 16  # every bottleneck's standalone ReLU
+        got = gr.run([x])[0]
+    finally:
+        gr.close()
+    assert np.array_equal(got, oracle.run(g, [x], uint8_mode=0)[g.outputs[0]])
+
+
 def test_pipelined_run_equals_unpipelined(ctx):
     """tb200_graph_run cuts the batch into chunks and overlaps H2D / kernels / D2H; same bytes as the single-chunk plan."""
     import os

@@ -197,3 +197,26 @@ def test_uint8_fc_uses_the_bias_tensors_own_scale(oracle, reference):
     g.layers[-1]["bias_scale"] = float(np.float32(0.02) * np.float32(0.004))
     other = oracle.run(g, [xin], uint8_mode=0)[y]
     assert np.abs(other.astype(int) - want[y].astype(int)).max() > 1, "test vacuous: the bias scale does not matter here"
+
+
+@pytest.mark.parametrize("dtype", [abi.DT_INT8, abi.DT_UINT8], ids=["int8", "uint8"])
+def test_yolov5s_reduced_every_layer(oracle, reference, dtype):
+    """C5 of BASELINE.json (YOLOv5s; int8 keeps SiLU as Sigmoid + Eltwise-PROD, uint8 uses HardSwish as the reference's
+    yolov5s-opt.py writes it) at reduced width / resolution: every layer of the oracle against the UNMODIFIED reference."""
+    g, b = workloads.yolov5s(dtype, batch=1, res=128, width=0.25, head=27, seed=3)
+    x = b.random_input(2)
+    want, _ = reference.run(g, [x], want=layer_outputs(g))
+    if dtype == abi.DT_INT8:
+        got = oracle.run(g, [x])
+        for li, L in enumerate(g.layers):
+            assert np.array_equal(got[L["output"]], want[L["output"]]), f"layer {li} {abi.OP_NAMES[L['op']]}"
+        assert all(len(np.unique(want[t])) > 20 for t in g.outputs)
+        return
+    from tests.helpers import single_layer_graph
+
+    want[g.inputs[0]] = x
+    for li, L in enumerate(g.layers):
+        h, src = single_layer_graph(g, li)
+        got = oracle.run(h, [want[t] for t in src])
+        d = np.abs(got[h.outputs[0]].astype(np.int32) - want[L["output"]].astype(np.int32))
+        assert d.max() <= 1, f"layer {li} {abi.OP_NAMES[L['op']]}: {int(d.max())} LSB"

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, multi-GPU trip (gpurun --gpus N): NCCL path of the single-process GPU group, bench under torchrun as the driver launches it,
+# C4 strong scaling (global batch 128 split over the GPUs), unmodified tm_benchmark on the group
+N=${1:-2}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/multi_gpus.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_tengine_integration.py -m gpu -q -p no:cacheprovider --timeout 600 > gpurun_out/pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_multi_${N}gpu.log
+grep -E "passed|failed|skipped" gpurun_out/pytest_multi_${N}gpu.log | tail -2; grep -E "^FAILED|^ERROR" gpurun_out/pytest_multi_${N}gpu.log | head
+NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_mobilenet_${N}gpu.log 2>&1
+tail -n 1 gpurun_out/bench_mobilenet_${N}gpu.log | cut -c1-1200
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --workload yolov3_tiny_uint8 --global-batch 128 > gpurun_out/bench_yolo_strong_${N}gpu.log 2>&1
+tail -n 1 gpurun_out/bench_yolo_strong_${N}gpu.log | cut -c1-1200
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 20 --warmup 3 --workload yolov5s_int8 --global-batch 64 > gpurun_out/bench_yolov5s_strong_${N}gpu.log 2>&1
+tail -n 1 gpurun_out/bench_yolov5s_strong_${N}gpu.log | cut -c1-600
+# the unmodified tm_benchmark on the whole group (environment selects the GPUs), batch 32 per GPU
+TG_B200_GPUS=$N timeout 300 build/tengine/tm_benchmark -d B200 -m oracle/_ref/models/mobilenet_v1_int8.tmfile -i $((32*N)),3,224,224 -f 2 -r 20 -t 8 > gpurun_out/tm_benchmark_${N}gpu.log 2>&1
+tail -n 3 gpurun_out/tm_benchmark_${N}gpu.log

@@ -12,7 +12,7 @@ from tengine_b200 import runtime as rt  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 net = sys.argv[2] if len(sys.argv) > 2 else "mobilenet_v1"
 dt = abi.DT_UINT8 if (len(sys.argv) > 3 and sys.argv[3] == "uint8") else abi.DT_INT8
-res = 416 if net == "yolov3_tiny" else 224
+res = 416 if net == "yolov3_tiny" else (640 if net == "yolov5s" else 224)
 g, b = getattr(workloads, net)(dt, batch=batch, res=res)
 ctx = rt.Context(0)
 graph = rt.Graph(ctx, g, abi.PRERUN_NO_GRAPH)
