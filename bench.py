@@ -224,9 +224,16 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def int8_tensor_peak():
-    """(TOPS, source): the on-box tcgen05 kind::i8 peak measured by the library's pure-MMA probe when it exists, else twice
-    the measured dense bf16 rate of MEASURED_PEAKS.json (kind::i8 issues at twice the bf16 rate), else the nominal 4500."""
+def int8_tensor_peak(ctx=None):
+    """(TOPS, source): the on-box tcgen05 kind::i8 peak measured live by the library's pure-MMA probe, else twice the measured
+    dense bf16 rate of MEASURED_PEAKS.json (kind::i8 issues at twice the bf16 rate), else the nominal 4500."""
+    if ctx is not None:
+        try:
+            t = ctx.probe_int8_tops()
+            if t > 100:
+                return t, "measured live: tcgen05.mma kind::i8 128x256x32 loop, one CTA per SM (tb200_probe_int8_tops)"
+        except Exception:
+            pass
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
@@ -396,7 +403,7 @@ def main():
             dom_bytes += L["weight"].size + (4 * g.dims(L["output"])[1] if L["bias"] is not None else 0)
             dom_ops += 2.0 * g.numel(L["output"]) * frac_of_batch * (L["weight"].size // g.dims(L["output"])[1])
     hbm_peak, hbm_src = measured_peaks()
-    tops_peak, tops_src = int8_tensor_peak()
+    tops_peak, tops_src = int8_tensor_peak(ctx)
     ridge = tops_peak * 1e12 / (hbm_peak * 1e9)  # op/B
     intensity = dom_ops / dom_bytes if dom_bytes else 0.0
     if intensity > ridge:

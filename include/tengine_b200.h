@@ -211,6 +211,10 @@ TB200_API int tb200_graph_postrun(tb200_graph* g);
  * batch is sharded over several GPUs; identical layout on every rank for identical graphs. */
 TB200_API int tb200_graph_weight_arena(tb200_graph* g, void** device_ptr, size_t* bytes);
 
+/* On-box peak of the int8 tensor pipe in TOP/s: a pure tcgen05.mma kind::i8 loop (128 x 256 x 32, one CTA per SM), the measured
+ * denominator of the tensor roofline that bench.py reports for compute-bound kernel families. */
+TB200_API int tb200_probe_int8_tops(tb200_context* ctx, double* tops);
+
 /* Packed-weight cache (the CPU analogue is conv_hcl_prerun's interleaved weights, conv_kernel_x86.c:2137-2209,
  * rebuilt at every prerun): with a directory set -- here or with TG_B200_PACK_CACHE -- prerun stores the packed arena image under a
  * hash of everything it depends on (descriptors, kernel choices, weights, biases, scales) and later preruns of the same model read
@@ -219,6 +223,10 @@ TB200_API int tb200_graph_weight_arena(tb200_graph* g, void** device_ptr, size_t
  * against the reference; int8 / uint8 weights are what its files carry.) */
 TB200_API int tb200_pack_cache_dir(const char* dir);
 TB200_API int tb200_graph_pack_cache_state(tb200_graph* g);
+
+/* The sharding rule (pure function, no GPU needed): images [first, first + num) of a batch of n belong to shard `rank` of `world`;
+ * contiguous slices of dim 0 of the NCHW buffers, the first n % world shards one image longer. */
+TB200_API int tb200_shard_range(int n_images, int world, int rank, int* first_image, int* num_images);
 
 /* multi-GPU contexts: re-send the arena (after a caller filled GPU 0's arena itself, TB200_PRERUN_NO_WEIGHTS) */
 TB200_API int tb200_graph_broadcast_weights(tb200_graph* g);

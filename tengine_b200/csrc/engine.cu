@@ -194,6 +194,7 @@ struct tb200_graph
     uint8_t* w_arena = nullptr;
     size_t w_bytes = 0;
     int chunks = 1;
+    std::vector<int> chunk_first, chunk_count; // images of pipeline chunk k: [first, first + count)
     std::vector<std::vector<Step>> chunk_steps;
     std::vector<cudaGraph_t> cu_graphs;
     std::vector<cudaGraphExec_t> cu_execs;
@@ -462,6 +463,11 @@ static int run_step(tb200_graph* g, const Step& s, cudaStream_t st)
     case K_POOL: err = launch_pool(s.in, s.out, s.ps, s.u8, st); break;
     case K_POINTWISE: err = launch_pointwise(s.in, s.in2, s.out, s.bytes, s.pp, s.u8, st); break;
     case K_CONCAT_PART:
+        if (s.scale == 1) // 16-channel-aligned input: vectorised, requantisation as a byte table (s.w; nullptr = equal quantisation)
+        {
+            err = launch_concat_lut(s.in, s.out, (const uint8_t*)s.w, s.npix, s.c, s.c_write, s.cp_in, s.cp_out, s.c_off, st);
+            break;
+        }
         err = launch_concat_part(s.in, s.out, s.npix, s.c, s.c_write, s.cp_in, s.cp_out, s.c_off, s.s_in, s.z_in, s.s_out, s.z_out, s.u8, st);
         break;
     case K_LUT: err = launch_byte_lut(s.in, s.out, (const uint8_t*)s.w, s.bytes, s.c, s.cp_in, st); break;
@@ -529,6 +535,32 @@ static void build_byte_lut(int op, bool u8, const tb200_tensor_desc& tin, const 
     }
 }
 
+// (leaky) ReLU as a byte table, with the arithmetic of relu/relu_kernel_ref_int8.c:41-94 and relu_kernel_ref_uint8.c:41-96 (the same
+// statements as kernels_direct.cu pointwise_exact_byte): used where the node is folded into the max pooling that follows it.
+static void build_relu_lut(bool u8, const tb200_tensor_desc& tin, const tb200_tensor_desc& tout, float slope, uint8_t* lut)
+{
+    for (int b = 0; b < 256; b++)
+    {
+        volatile float f0 = u8 ? (float)(b - tin.zero_point) * tin.scale : (float)(int)(int8_t)b * tin.scale;
+        volatile float f = (f0 < 0.f) ? ((slope == 0.f) ? 0.f : f0 * slope) : f0;
+        int q;
+        if (u8)
+        {
+            volatile float t = f / tout.scale;
+            volatile float tz = t + (float)tout.zero_point; // relu_kernel_ref_uint8.c:85: the zero point is added inside round()
+            q = (int)roundf(tz);
+            q = q > 255 ? 255 : (q < 0 ? 0 : q);
+        }
+        else
+        {
+            volatile float t = f / tout.scale;
+            q = (int)roundf(t);
+            q = q > 127 ? 127 : (q < -127 ? -127 : q);
+        }
+        lut[b] = (uint8_t)(q & 0xff);
+    }
+}
+
 static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int num_tensors, const tb200_layer_desc* layers, int num_layers,
                       const int32_t* input_ids, int num_inputs, const int32_t* output_ids, int num_outputs, int flags, tb200_graph* g)
 {
@@ -566,6 +598,34 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             if (!same) continue;
             fused[li].output = R.output, post_relu[li] = 1;
             fused[lj].op = TB200_OP_NOP_, fused[lj].num_inputs = 0;
+        }
+    }
+    // (Leaky) ReLU -> max pooling whose output keeps the ReLU's quantisation, the ReLU result having no other reader: the ReLU is
+    // a non-decreasing byte table, so max(table(x)) == table(max(x)); the pooling reads the convolution's bytes and applies the
+    // table to each window's maximum.  One pass over the big tensor disappears (pool_relu[pool layer] = the folded ReLU layer).
+    std::vector<int> pool_relu(num_layers, -1);
+    if (!(flags & TB200_PRERUN_NO_GRAPH) && !getenv("TB200_NO_FUSION"))
+    {
+        std::vector<int> readers(num_tensors, 0), reader_layer(num_tensors, -1);
+        for (int li = 0; li < num_layers; li++)
+            for (int k = 0; k < fused[li].num_inputs && k < 4; k++)
+                if (fused[li].inputs[k] >= 0 && fused[li].inputs[k] < num_tensors) readers[fused[li].inputs[k]]++, reader_layer[fused[li].inputs[k]] = li;
+        std::vector<char> is_out(num_tensors, 0);
+        for (int i = 0; i < num_outputs; i++)
+            if (output_ids[i] >= 0 && output_ids[i] < num_tensors) is_out[output_ids[i]] = 1;
+        for (int li = 0; li < num_layers; li++)
+        {
+            const tb200_layer_desc& R = fused[li];
+            if (R.op != TB200_OP_RELU || R.output < 0 || R.output >= num_tensors || readers[R.output] != 1 || is_out[R.output]) continue;
+            if (!(R.negative_slope >= 0.f && R.negative_slope <= 1.f)) continue; // the table must be non-decreasing
+            const int lj = reader_layer[R.output];
+            const tb200_layer_desc& P = fused[lj];
+            if (lj <= li || P.op != TB200_OP_POOL || P.pool_method != TB200_POOL_MAX || P.output < 0 || P.output >= num_tensors) continue;
+            const tb200_tensor_desc &tr = tensors[R.output], &tp = tensors[P.output];
+            if (tr.scale != tp.scale || tr.zero_point != tp.zero_point || tr.data_type != tp.data_type) continue;
+            pool_relu[lj] = li;
+            fused[lj].inputs[0] = R.inputs[0]; // the pooling reads what the ReLU read
+            fused[li].op = TB200_OP_NOP_, fused[li].num_inputs = 0;
         }
     }
     layers = fused.data();
@@ -733,10 +793,15 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             if (u8 && kind[li] == K_IGEMM) // [border patterns][OCp] int32, see the packing below
                 wtotal += align_up((size_t)(L.pad_h0 + 1) * (L.kernel_h + 1) * (L.pad_w0 + 1) * (L.kernel_w + 1) * tout.cp * 4, 256);
         }
-        if (kind[li] == K_LUT)
+        if (kind[li] == K_LUT || (kind[li] == K_POOL && pool_relu[li] >= 0))
         {
             blobs[li].w_off = wtotal; // 256-byte table; part of the arena so that it travels with the single broadcast
             wtotal += 256;
+        }
+        if (kind[li] == K_CONCAT_PART)
+        {
+            blobs[li].w_off = wtotal; // one requantisation table per input
+            wtotal += 256 * 4;
         }
         // which graph inputs need an NHWC copy (everything except a stem conv reads NHWC)
         for (int k = 0; k < L.num_inputs; k++)
@@ -969,6 +1034,44 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
         for (int li = 0; li < num_layers && !cache_hit; li++)
         {
             const tb200_layer_desc& L = layers[li];
+            if (kind[li] == K_CONCAT_PART)
+            {
+                // per-input requantisation of concat_kernel_ref_int8.c:70-80 (roundf(q * (s_in / s_out)), including its clamp of
+                // values below -127 to +127) and concat_kernel_ref_uint8.c (dequantise, round(f / s_out) + zp, clamp) as byte tables
+                const tb200_tensor_desc& to = g->tensors[L.output].d;
+                for (int k = 0; k < L.num_inputs && k < 4; k++)
+                {
+                    const tb200_tensor_desc& ti = g->tensors[L.inputs[k]].d;
+                    uint8_t* lut = img.data() + blobs[li].w_off + 256 * k;
+                    for (int b = 0; b < 256; b++)
+                    {
+                        int q;
+                        if (ti.data_type == TB200_DT_UINT8)
+                        {
+                            volatile float f = ((float)b - (float)ti.zero_point) * ti.scale;
+                            volatile float t = f / to.scale;
+                            q = (int)roundf(t) + to.zero_point;
+                            q = q > 255 ? 255 : (q < 0 ? 0 : q);
+                        }
+                        else
+                        {
+                            volatile float rs = ti.scale / to.scale;
+                            volatile float t = (float)(int)(int8_t)b * rs;
+                            q = (int)roundf(t);
+                            q = (q > 127 ? 127 : (q < -127 ? 127 : q)) & 0xff; // sic
+                        }
+                        lut[b] = (uint8_t)q;
+                    }
+                }
+                continue;
+            }
+            if (kind[li] == K_POOL && pool_relu[li] >= 0)
+            {
+                // tin = what the folded ReLU read, its own output quantisation = the pooling's
+                build_relu_lut(g->tensors[L.inputs[0]].d.data_type == TB200_DT_UINT8, g->tensors[L.inputs[0]].d, g->tensors[L.output].d,
+                               layers[pool_relu[li]].negative_slope, img.data() + blobs[li].w_off);
+                continue;
+            }
             if (kind[li] == K_LUT)
             {
                 build_byte_lut(L.op, g->tensors[L.inputs[0]].d.data_type == TB200_DT_UINT8, g->tensors[L.inputs[0]].d, g->tensors[L.output].d,
@@ -1161,6 +1264,15 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                 const tb200_layer_desc& L = layers[li];
                 if (L.op != TB200_OP_CONV && L.op != TB200_OP_FC) continue;
                 const int ocp = g->tensors[L.output].cp;
+                {
+                    const float* fmv = (const float*)(img.data() + blobs[li].fast_off);
+                    const TensorInfo& ti = g->tensors[L.inputs[0]];
+                    const TensorInfo& to = g->tensors[L.output];
+                    int y0, y1;
+                    memcpy(&y0, fmv + 2, 4), memcpy(&y1, fmv + 3, 4);
+                    fprintf(stderr, "[tb200 dbg] pack layer %d consts: in(%.9g, %d) out(%.9g, %d) ws %.9g wz %d M %.9g %.9g y %d %d bias0 %d\n", li, ti.d.scale, ti.d.zero_point,
+                            to.d.scale, to.d.zero_point, L.weight_scales[0], L.weight_zero, fmv[0], fmv[1], y0, y1, L.bias ? L.bias[0] : 0);
+                }
                 fprintf(stderr, "[tb200 dbg] pack layer %d kind %d: w %016llx (%zu) bias %016llx scale %016llx fast %016llx fuse %d fast_int %d u8fast %d\n", li, kind[li],
                         fnv(img.data() + blobs[li].w_off, blobs[li].w_size), blobs[li].w_size, fnv(img.data() + blobs[li].bias_off, (size_t)ocp * 4),
                         fnv(img.data() + blobs[li].scale_off, (size_t)ocp * 4), fnv(img.data() + blobs[li].fast_off, (size_t)ocp * 8), fuse_bias[li], fast_int_ok[li],
@@ -1189,26 +1301,59 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
     bool same_batch = true;
     for (auto& t : g->tensors) same_batch &= (t.d.dims[0] == Ntot);
     int K = 1;
+    std::vector<int> cfirst{0}, ccount{Ntot};
     if (same_batch && !(flags & TB200_PRERUN_NO_GRAPH))
     {
         K = Ntot >= 32 ? 2 : 1;
         if (const char* ev = getenv("TB200_PIPELINE_CHUNKS")) K = atoi(ev) > 0 ? atoi(ev) : K;
         while (K > 1 && Ntot % K) K--;
+        cfirst.clear(), ccount.clear();
+        for (int k = 0; k < K; k++) cfirst.push_back(k * (Ntot / K)), ccount.push_back(Ntot / K);
+        if (K == 2 && Ntot >= 64 && !getenv("TB200_PIPELINE_CHUNKS"))
+        {
+            // two chunks of 1/4 and 3/4: the kernels only ever wait for the first quarter of the input (measured on MobileNet-v1
+            // b=256 through tb200_graph_run: 1.78 ms vs 1.92 ms for two halves; three-way splits 1.85-1.87 ms)
+            const int a = ((Ntot / 4 + 7) / 8) * 8;
+            cfirst = {0, a}, ccount = {a, Ntot - a};
+        }
+        // TB200_PIPELINE_SPLIT="40,88,128": explicit (uneven) chunk sizes in images -- a small first chunk shortens the time the
+        // kernels wait for the first H2D copy; must sum to the batch
+        if (const char* ev = getenv("TB200_PIPELINE_SPLIT"))
+        {
+            std::vector<int> sz;
+            int sum = 0;
+            for (const char* p = ev; *p;)
+            {
+                char* end;
+                const long v = strtol(p, &end, 10);
+                if (end == p || v <= 0) break;
+                sz.push_back((int)v), sum += (int)v;
+                p = (*end == ',') ? end + 1 : end;
+            }
+            if (sum == Ntot && sz.size() >= 1 && sz.size() <= 16)
+            {
+                cfirst.clear(), ccount.clear(), K = (int)sz.size();
+                int f = 0;
+                for (int v : sz) cfirst.push_back(f), ccount.push_back(v), f += v;
+            }
+        }
     }
     const int Kpipe = K;
     g->chunks = Kpipe;
+    g->chunk_first = cfirst, g->chunk_count = ccount;
     g->chunk_steps.resize(Kpipe > 1 ? Kpipe : 0);
-    // builds the launch sequence of chunk `ck` of `K` (K == 1: the whole batch) into `steps`
-    auto build_steps = [&](const int K, const int ck, std::vector<Step>& steps, const bool count_work) -> int
+    // builds the launch sequence of images [first, first + nb) (the whole batch, or one pipeline chunk) into `steps`
+    auto build_steps = [&](const int first, const int nb, std::vector<Step>& steps, const bool count_work) -> int
     {
-        const int nb = Ntot / K;
-        auto tdev = [&](const TensorInfo& t) -> uint8_t* { return t.dev + (size_t)ck * (t.nhwc_bytes / K); };
+        // byte offset of image `first` inside a tensor of the whole batch
+        auto img_off = [&](size_t total_bytes) -> size_t { return (total_bytes / (size_t)Ntot) * (size_t)first; };
+        auto tdev = [&](const TensorInfo& t) -> uint8_t* { return t.dev + img_off(t.nhwc_bytes); };
         for (size_t i = 0; i < g->input_ids.size(); i++)
         {
             TensorInfo& t = g->tensors[g->input_ids[i]];
             if (!t.nhwc_needed) continue;
             Step s;
-            s.kind = K_NCHW2NHWC, s.layer = -1, s.in = g->in_nchw_dev[i] + ck * (t.nchw_bytes / K), s.out = tdev(t);
+            s.kind = K_NCHW2NHWC, s.layer = -1, s.in = g->in_nchw_dev[i] + img_off(t.nchw_bytes), s.out = tdev(t);
             s.n = nb, s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
             steps.push_back(s);
         }
@@ -1266,7 +1411,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     }
                 }
                 if (s.kind == K_CONV_STEM || s.kind == K_STEM_TC || (s.kind == K_GATHER_TC && tin.input_index >= 0 && C <= 3))
-                    s.in = g->in_nchw_dev[tin.input_index] + ck * (tin.nchw_bytes / K);
+                    s.in = g->in_nchw_dev[tin.input_index] + img_off(tin.nchw_bytes);
                 s.nhwc16 = (s.kind == K_GATHER_TC && !(tin.input_index >= 0 && C <= 3)) ? 1 : 0;
                 if (s.kind == K_STEM_TC) stem_plan_create(&s.dwp, s.in, s.cs); // falls back to the global-memory gather
                 if (s.kind == K_GATHER_TC)
@@ -1296,6 +1441,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                 p.method = L.pool_method, p.caffe_flavor = L.caffe_flavor;
                 p.in_scale = tin.d.scale, p.out_scale = tout.d.scale, p.in_zero = tin.d.zero_point, p.out_zero = tout.d.zero_point;
                 if (L.pool_global) p.kh = H, p.kw = W, p.sh = p.sw = 1, p.ph0 = p.pw0 = 0;
+                p.lut = pool_relu[li] >= 0 ? g->w_arena + blobs[li].w_off : nullptr, p.c_real = u8 ? C : tin.cp;
                 if (tout.d.dims[1] != C) return bail(fail(TB200_ERR_INVALID, "layer %d: pool channel mismatch", li));
             }
             else if (L.op == TB200_OP_RELU || L.op == TB200_OP_ELTWISE)
@@ -1315,7 +1461,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     p.scale1 = t1.d.scale, p.zero1 = t1.d.zero_point;
                     s.in2 = tdev(t1);
                 }
-                s.bytes = (long long)(tin.nhwc_bytes / K);
+                s.bytes = (long long)(tin.nhwc_bytes / (size_t)Ntot * (size_t)nb);
                 if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: pointwise shape mismatch", li));
             }
             else if (L.op == TB200_OP_CONCAT && L.num_inputs > 1)
@@ -1329,6 +1475,9 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     p.npix = (long long)N * H * W, p.c = tk.d.dims[1], p.cp_in = tk.cp, p.cp_out = tout.cp, p.c_off = coff;
                     p.s_in = tk.d.scale, p.z_in = tk.d.zero_point, p.s_out = tout.d.scale, p.z_out = tout.d.zero_point;
                     p.c_write = (k + 1 == L.num_inputs) ? tout.cp - coff : tk.d.dims[1];
+                    // vectorised table path when everything is 16-channel aligned; identical quantisation -> no table at all
+                    p.scale = (tk.d.dims[1] % 16 == 0 && coff % 16 == 0 && !getenv("TB200_CONCAT_BYTEWISE")) ? 1 : 0;
+                    p.w = (tk.d.scale == tout.d.scale && tk.d.zero_point == tout.d.zero_point) ? nullptr : g->w_arena + blobs[li].w_off + 256 * k;
                     coff += tk.d.dims[1];
                     if (k + 1 < L.num_inputs) steps.push_back(p);
                     else s = p;
@@ -1343,7 +1492,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             else if (s.kind == K_LUT)
             {
                 s.w = g->w_arena + blobs[li].w_off;
-                s.bytes = (long long)(tin.nhwc_bytes / K);
+                s.bytes = (long long)(tin.nhwc_bytes / (size_t)Ntot * (size_t)nb);
                 s.c = C, s.cp_in = tin.cp;
                 if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_INVALID, "layer %d: unary op changes the shape", li));
             }
@@ -1360,7 +1509,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             }
             else if (L.op == TB200_OP_IDENTITY || L.op == TB200_OP_CONCAT || L.op == TB200_OP_RESHAPE)
             {
-                s.bytes = (long long)(tin.nhwc_bytes / K);
+                s.bytes = (long long)(tin.nhwc_bytes / (size_t)Ntot * (size_t)nb);
                 if (tout.nhwc_bytes != tin.nhwc_bytes) return bail(fail(TB200_ERR_UNSUPPORTED, "layer %d: identity changes the NHWC footprint", li));
             }
             g->layer_kernel[li] = (s.kind == K_CONV_DW && s.dwp.valid) ? "conv_dw3x3_tma_dp4a" : ((s.kind == K_GATHER_TC && s.wp.valid) ? "conv_window_tcgen05" : kStepName[s.kind]);
@@ -1370,7 +1519,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
         {
             TensorInfo& t = g->tensors[g->output_ids[i]];
             Step s;
-            s.kind = K_NHWC2NCHW, s.layer = -1, s.in = tdev(t), s.out = g->out_nchw_dev[i] + ck * (t.nchw_bytes / K);
+            s.kind = K_NHWC2NCHW, s.layer = -1, s.in = tdev(t), s.out = g->out_nchw_dev[i] + img_off(t.nchw_bytes);
             s.n = nb, s.c = t.d.dims[1], s.h = t.d.dims[2], s.w_ = t.d.dims[3];
             steps.push_back(s);
         }
@@ -1379,10 +1528,10 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
     // the whole-batch plan serves tb200_graph_launch / profile (device-resident use); the chunk plans serve the pipelined
     // tb200_graph_run.  They address the same tensors (a chunk is a slice of dim 0), so either may run at any time.
     {
-        int rc = build_steps(1, 0, g->steps, true);
+        int rc = build_steps(0, Ntot, g->steps, true);
         if (rc) return rc;
         for (int ck = 0; ck < (int)g->chunk_steps.size(); ck++)
-            if ((rc = build_steps(Kpipe, ck, g->chunk_steps[ck], false)) != 0) return rc;
+            if ((rc = build_steps(cfirst[ck], ccount[ck], g->chunk_steps[ck], false)) != 0) return rc;
     }
     g->num_launches = (int)g->steps.size();
     for (const Step& st : g->steps) g->num_launches += st.kind == K_RESHAPE ? 1 : 0; // two layout kernels
@@ -1570,7 +1719,8 @@ int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* tensors, int
     int first = 0;
     for (int r = 0; r < R; r++)
     {
-        const int count = N / R + (r < N % R ? 1 : 0);
+        int count = 0;
+        tb200_shard_range(N, R, r, nullptr, &count);
         for (auto& t : td) t.dims[0] = count;
         tb200_graph* sh = nullptr;
         tb200_context* c = r == 0 ? ctx : ctx->peers[r - 1];
@@ -1602,10 +1752,29 @@ int tb200_graph_prerun(tb200_context* ctx, const tb200_tensor_desc* tensors, int
     return 0;
 }
 
+// how a batch of n images is cut over `world` GPUs: contiguous slices of dim 0, the first n % world shards one image longer
+int tb200_shard_range(int n_images, int world, int rank, int* first_image, int* num_images)
+{
+    if (n_images < 0 || world < 1 || rank < 0 || rank >= world) return fail(TB200_ERR_INVALID, "bad shard arguments");
+    const int base = n_images / world, extra = n_images % world;
+    if (first_image) *first_image = rank * base + (rank < extra ? rank : extra);
+    if (num_images) *num_images = base + (rank < extra ? 1 : 0);
+    return 0;
+}
+
 int tb200_graph_broadcast_weights(tb200_graph* g)
 {
     if (!g) return fail(TB200_ERR_INVALID, "null graph");
     return broadcast_arena(g);
+}
+
+int tb200_probe_int8_tops(tb200_context* ctx, double* tops)
+{
+    if (!ctx || !tops) return fail(TB200_ERR_INVALID, "bad arguments");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    const cudaError_t e = probe_int8_mma_peak(ctx->num_sms, tops, ctx->stream);
+    if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "int8 MMA probe: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int tb200_pack_cache_dir(const char* dir)
@@ -1755,9 +1924,9 @@ static int run_enqueue_h2d(tb200_graph* g, const void* const* host_inputs)
         for (size_t i = 0; i < g->input_ids.size(); i++)
         {
             const int id = g->input_ids[i];
-            const size_t bytes = g->tensors[id].nchw_bytes / K;
-            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i] + ck * bytes, (const uint8_t*)host_inputs[i] + (size_t)g->first_image * image_bytes(g, id) + ck * bytes,
-                                    bytes, cudaMemcpyHostToDevice, g->copy_stream));
+            const size_t ib = image_bytes(g, id), off = ib * (size_t)g->chunk_first[ck], bytes = ib * (size_t)g->chunk_count[ck];
+            CUDA_OK(cudaMemcpyAsync(g->in_nchw_dev[i] + off, (const uint8_t*)host_inputs[i] + (size_t)g->first_image * ib + off, bytes, cudaMemcpyHostToDevice,
+                                    g->copy_stream));
         }
         CUDA_OK(cudaEventRecord(g->ev_in[ck], g->copy_stream));
     }
@@ -1791,9 +1960,9 @@ static int run_enqueue_compute(tb200_graph* g, void* const* host_outputs)
         for (size_t i = 0; i < g->output_ids.size(); i++)
         {
             const int id = g->output_ids[i];
-            const size_t bytes = g->tensors[id].nchw_bytes / K;
-            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + (size_t)g->first_image * image_bytes(g, id) + ck * bytes, g->out_nchw_dev[i] + ck * bytes, bytes,
-                                    cudaMemcpyDeviceToHost, g->d2h_stream));
+            const size_t ib = image_bytes(g, id), off = ib * (size_t)g->chunk_first[ck], bytes = ib * (size_t)g->chunk_count[ck];
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)host_outputs[i] + (size_t)g->first_image * ib + off, g->out_nchw_dev[i] + off, bytes, cudaMemcpyDeviceToHost,
+                                    g->d2h_stream));
         }
     }
     return 0;

@@ -1279,6 +1279,75 @@ __global__ void __launch_bounds__(128) gemm_simple_kernel(const __grid_constant_
     }
 }
 
+// ---- on-box peak of the int8 tensor pipe ("replace the nominal numbers by on-box microbenchmark peaks") ---------
+// One CTA per SM; one thread issues `iters` x 4 tcgen05.mma.kind::i8 of 128 x 256 x 32 on fixed shared-memory tiles (contents
+// irrelevant), alternating between two TMEM accumulators; no loads, no epilogue.  ops = CTAs * iters * 4 * 2 * 128 * 256 * 32.
+__global__ void __launch_bounds__(128) i8_mma_peak_kernel(int iters, uint32_t idesc)
+{
+    extern __shared__ __align__(1024) uint8_t peak_smem[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(peak_smem) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t done;
+    __shared__ uint32_t tmem_slot;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += 128) sts_u4(smem_u32(sm) + i * 16, 0x01010101u, 0x01020304u, 0x7f7f0101u, 0u);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0)
+    {
+        const uint64_t da = make_smem_desc(smem_u32(sm), 128), db = make_smem_desc(smem_u32(sm) + 16384u, 128);
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) umma_i8(tmem + (uint32_t)(it & 1) * 256u, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+        tcgen05_commit(&done);
+        mbar_wait(&done, 0);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+cudaError_t probe_int8_mma_peak(int num_sms, double* tops, cudaStream_t st)
+{
+    cudaError_t err = cudaFuncSetAttribute(i8_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (err != cudaSuccess) return err;
+    const uint32_t idesc = make_idesc_i8(256, true, true);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    const int iters = 20000;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++)
+    {
+        cudaEventRecord(a, st);
+        i8_mma_peak_kernel<<<num_sms, 128, 16384 + 32768 + 1024, st>>>(iters, idesc);
+        cudaEventRecord(b, st);
+        if ((err = cudaEventSynchronize(b)) != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double t = (double)num_sms * iters * 4.0 * 2.0 * 128 * 256 * 32 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t; // the first repetition is the warm-up
+    }
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    *tops = best;
+    return err;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1402,7 +1471,7 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
     p->k_blocks = (k + p->block_k - 1) / p->block_k;
     p->u8 = u8 != 0; // u8 = 1 + weight zero point for uint8 layers
     p->b_signed = !p->u8 || u8 != 1;
-    p->cplane = (p->u8 && u8 != 1) ? 128 - (u8 - 1) : 0;
+    p->cplane = (p->u8 && u8 != 1 && !getenv("TB200_DEBUG_NO_CPLANE")) ? 128 - (u8 - 1) : 0; // (debug switch: WRONG results, timing experiments only)
     p->block_n = gemm_block_n(ocp, u8);
     p->bnx = p->block_n;
     p->taps = 1;
@@ -1462,7 +1531,7 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out,
     p->k = taps * s.cp;
     p->u8 = u8 != 0; // u8 = 1 + weight zero point for uint8 layers
     p->b_signed = !p->u8 || u8 != 1;
-    p->cplane = (p->u8 && u8 != 1) ? 128 - (u8 - 1) : 0;
+    p->cplane = (p->u8 && u8 != 1 && !getenv("TB200_DEBUG_NO_CPLANE")) ? 128 - (u8 - 1) : 0; // (debug switch: WRONG results, timing experiments only)
     p->block_n = gemm_block_n(s.ocp, u8);
     p->bnx = p->block_n;
     p->taps = taps, p->in_h = s.h, p->in_w = s.w;

@@ -22,6 +22,8 @@ struct PoolShape
     int method, caffe_flavor;
     float in_scale, out_scale;
     int in_zero, out_zero;
+    const uint8_t* lut; // a (leaky) ReLU node folded in front of a same-scale max pooling: applied to the window's maximum (engine.cu)
+    int c_real;         // uint8 with lut: channels >= c_real are pad lanes and stay 0
 };
 
 struct PointwiseParams
@@ -47,6 +49,7 @@ cudaError_t launch_byte_lut(const void* in, void* out, const uint8_t* lut, long 
 // softmax over the channel axis (softmax_kernel_ref_int8.c / _uint8.c), one thread per pixel
 cudaError_t launch_softmax(const void* in, void* out, long long npix, int c, int cp, float s_in, int z_in, float s_out, int z_out, bool u8,
                            cudaStream_t st);
+cudaError_t launch_concat_lut(const void* in, void* out, const uint8_t* lut, long long npix, int c, int c_write, int cp_in, int cp_out, int c_off, cudaStream_t st);
 cudaError_t launch_upsample(const void* in, void* out, int n, int h, int w, int cp, int scale, cudaStream_t st);
 cudaError_t launch_nchw_to_nhwc(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
 cudaError_t launch_nhwc_to_nchw(const void* in, void* out, int n, int c, int h, int w, cudaStream_t st);
@@ -137,5 +140,7 @@ cudaError_t launch_stem_tc(const DwPlan& plan, const void* in, const void* w, vo
 // 3x3 convolutions whose K the threads gather themselves (uint8 NCHW stems, 16-channel NHWC inputs), gemm_tcgen05.cu
 cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, const ConvShape& s, const EpiParams& e, int nhwc16, cudaStream_t st);
 cudaError_t launch_gemm_i8(const GemmPlan& plan, const EpiParams& e, const int32_t* btab, int num_sms, cudaStream_t st);
+// measured peak of tcgen05.mma kind::i8 (cta_group::1, 128 x 256 x 32) on this GPU, in TOP/s: the tensor roofline's denominator
+cudaError_t probe_int8_mma_peak(int num_sms, double* tops, cudaStream_t st);
 
 } // namespace tb200

@@ -772,6 +772,15 @@ cudaError_t launch_conv_stem(const void* in, const void* w, void* out, const Con
 template <bool U8>
 __global__ void __launch_bounds__(256) pool_max_same_scale_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolShape p)
 {
+    // p.lut: a (leaky) ReLU that preceded the pooling in the graph, as a byte table.  relu -> max == max -> relu because the
+    // table is non-decreasing in the (signed / unsigned) byte order, so it is applied ONCE per output to the window's maximum
+    // instead of to every input byte in a pass of its own (YOLOv3-tiny: conv -> leaky ReLU -> 2x2 max pool, six times).
+    __shared__ uint8_t tab[256];
+    if (p.lut)
+    {
+        tab[threadIdx.x] = __ldg(p.lut + threadIdx.x);
+        __syncthreads();
+    }
     const int cv = p.cp / 16;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned total = (unsigned)(p.n * p.oh * p.ow * cv);
@@ -793,12 +802,29 @@ __global__ void __launch_bounds__(256) pool_max_same_scale_kernel(const uint4* _
             else m = make_uint4(__vmaxs4(m.x, v.x), __vmaxs4(m.y, v.y), __vmaxs4(m.z, v.z), __vmaxs4(m.w, v.w));
         }
     if (!U8) m = make_uint4(__vmaxs4(m.x, 0x81818181u), __vmaxs4(m.y, 0x81818181u), __vmaxs4(m.z, 0x81818181u), __vmaxs4(m.w, 0x81818181u));
+    if (p.lut)
+    {
+        uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            uint32_t r = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+            {
+                const uint32_t y = (c16 * 16 + j * 4 + t < p.c_real) ? (uint32_t)tab[(w[j] >> (8 * t)) & 0xffu] : 0u;
+                r |= y << (8 * t);
+            }
+            w[j] = r;
+        }
+        m = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     out[(size_t)pix * cv + c16] = m;
 }
 
 cudaError_t launch_pool(const void* in, void* out, const PoolShape& p, bool u8, cudaStream_t st)
 {
-    if (p.method == TB200_POOL_MAX && p.in_scale == p.out_scale && (!u8 || p.in_zero == p.out_zero) && !getenv("TB200_POOL_EXACT"))
+    if (p.method == TB200_POOL_MAX && (p.lut || (p.in_scale == p.out_scale && (!u8 || p.in_zero == p.out_zero) && !getenv("TB200_POOL_EXACT"))))
     {
         const long long tot = (long long)p.n * p.oh * p.ow * (p.cp / 16);
         TB200_CHECK_32BIT(tot * 16);
@@ -879,6 +905,48 @@ cudaError_t launch_pointwise(const void* a, const void* b, void* out, long long 
     }
     if (u8) pointwise_kernel<true><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
     else pointwise_kernel<false><<<blocks_for(nvec, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec, p);
+    return cudaGetLastError();
+}
+
+// Vectorised form for 16-channel-aligned inputs: the per-input requantisation of concat_kernel_ref_{int8,uint8}.c is a function of one
+// byte, so it is a 256-entry table (built by engine.cu with the reference's arithmetic; nullptr = identity: equal quantisation).
+// Thread = 16 channels of one pixel; the last input also clears the output's pad lanes (vectors beyond its channels).
+__global__ void __launch_bounds__(256) concat_lut_kernel(const uint4* __restrict__ in, uint8_t* __restrict__ out, const uint8_t* __restrict__ lut, long long npix,
+                                                         int cv_in, int cv_write, int cp_in, int cp_out, int c_off)
+{
+    __shared__ uint8_t tab[256];
+    if (lut)
+    {
+        tab[threadIdx.x] = __ldg(lut + threadIdx.x);
+        __syncthreads();
+    }
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * cv_write) return;
+    const long long pix = idx / cv_write;
+    const int v = (int)(idx - pix * cv_write);
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (v < cv_in)
+    {
+        r = __ldg(in + (size_t)pix * (cp_in / 16) + v);
+        if (lut)
+        {
+            uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                w[j] = (uint32_t)tab[w[j] & 0xffu] | ((uint32_t)tab[(w[j] >> 8) & 0xffu] << 8) | ((uint32_t)tab[(w[j] >> 16) & 0xffu] << 16) |
+                       ((uint32_t)tab[w[j] >> 24] << 24);
+            r = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)pix * cp_out + c_off + v * 16) = r;
+}
+
+cudaError_t launch_concat_lut(const void* in, void* out, const uint8_t* lut, long long npix, int c, int c_write, int cp_in, int cp_out, int c_off, cudaStream_t st)
+{
+    if ((c % 16) || (c_off % 16) || (c_write % 16)) return cudaErrorInvalidValue;
+    const long long total = npix * (c_write / 16);
+    TB200_CHECK_32BIT(total * 16);
+    concat_lut_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, (uint8_t*)out, lut, npix, c / 16, c_write / 16, cp_in, cp_out, c_off);
     return cudaGetLastError();
 }
 

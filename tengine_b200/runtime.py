@@ -88,6 +88,13 @@ def set_pack_cache_dir(path):
     lib().tb200_pack_cache_dir(path.encode() if path else None)
 
 
+def shard_range(n_images, world, rank):
+    """(first image, number of images) of shard `rank` of `world` for a batch of n_images: the library's own rule."""
+    f, c = C.c_int(), C.c_int()
+    _check(lib().tb200_shard_range(int(n_images), int(world), int(rank), C.byref(f), C.byref(c)))
+    return f.value, c.value
+
+
 def device_count():
     return lib().tb200_device_count()
 
@@ -117,6 +124,13 @@ class Context:
 
     def stream_of(self, index):
         return lib().tb200_context_stream_of(self.h, int(index))
+
+    def probe_int8_tops(self):
+        """Measured peak of the int8 tensor pipe of GPU 0 of this context in TOP/s (tb200_probe_int8_tops)."""
+        t = C.c_double()
+        lib().tb200_probe_int8_tops.argtypes = [C.c_void_p, C.c_void_p]
+        _check(lib().tb200_probe_int8_tops(self.h, C.byref(t)))
+        return t.value
 
     @property
     def broadcast_kind(self):

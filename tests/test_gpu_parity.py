@@ -354,5 +354,12 @@ def test_pipelined_run_equals_unpipelined(ctx):
             gr.close()
         finally:
             os.environ.pop("TB200_PIPELINE_CHUNKS", None)
+    os.environ["TB200_PIPELINE_SPLIT"] = "5,11,16"  # uneven chunks
+    try:
+        gr = rt.Graph(ctx, g)
+        outs.append(gr.run([x])[0])
+        gr.close()
+    finally:
+        os.environ.pop("TB200_PIPELINE_SPLIT", None)
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])

@@ -1,24 +1,28 @@
-"""Host-side logic of the N>1 path with world_size 2 on CPU (gloo): contiguous batch sharding, the single weight-arena
-broadcast, max-over-ranks timing, and the property the sharding relies on -- images are independent units, so running
-the shards separately and concatenating equals running the whole batch (checked with the CPU oracle)."""
+"""Host-side logic of the N > 1 path on CPU.  The product shards a batch over several GPUs inside ONE process (a tb200 context
+over a GPU group, tests/test_gpu_multi.py); what can be checked without a GPU is (a) the library's sharding rule
+(tb200_shard_range: contiguous slices of dim 0, sizes differing by at most one), (b) the property the sharding relies on --
+images are independent units, so computing the slices separately and laying them side by side equals computing the whole batch --
+with two processes (world_size 2, gloo) each taking the slice the library assigns to it and the CPU oracle as the checker, and
+(c) the rank protocol of bench.py under torchrun: rank 0 drives the GPUs, every other rank only meets it at the barriers."""
 import os
 import socket
 
 import numpy as np
-import pytest
 
-from tengine_b200 import abi, sharding, workloads
+from tengine_b200 import abi, workloads
 
 
 def test_shard_ranges_partition_the_batch():
+    from tengine_b200 import runtime as rt
+
     for n in (1, 2, 7, 64, 128, 256, 257):
         for world in (1, 2, 3, 4, 8):
             seen = []
             for r in range(world):
-                s, c = sharding.shard_range(n, world, r)
+                s, c = rt.shard_range(n, world, r)
                 seen += list(range(s, s + c))
             assert seen == list(range(n)), (n, world)
-            sizes = [sharding.shard_range(n, world, r)[1] for r in range(world)]
+            sizes = [rt.shard_range(n, world, r)[1] for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
 
 
@@ -39,29 +43,27 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle.pyoracle import Oracle
+        from tengine_b200 import runtime as rt
 
-        # (1) the one-time weight broadcast: rank 0 holds the packed arena, the others an empty one of the same size
-        rng = np.random.default_rng(0)
-        arena0 = rng.integers(0, 256, 4096 + 13).astype(np.uint8)
-        arena = torch.from_numpy(arena0.copy() if rank == 0 else np.zeros_like(arena0))
-        sharding.broadcast_arena(arena, src=0)
-        ok_arena = bool(np.array_equal(arena.numpy(), arena0))
-        # (2) every rank runs ITS slice of the global batch (no collective in the steady state)
+        # every rank computes ITS slice of the global batch (no collective on the data path) ...
         n_global = 5
         gfull, b = workloads.tiny_net(abi.DT_INT8, batch=n_global, seed=3)
         x = b.random_input(11)
-        start, count = sharding.shard_range(n_global, world, rank)
+        start, count = rt.shard_range(n_global, world, rank)
         gshard, _ = workloads.tiny_net(abi.DT_INT8, batch=count, seed=3)
-        y = Oracle().run(gshard, [x[start:start + count]])
-        out = y[gshard.outputs[0]]
-        # (3) timing reduction
-        mx = sharding.max_over_ranks([10.0 + rank, 5.0 - rank])
-        q.put((rank, ok_arena, start, out, mx))
+        out = Oracle().run(gshard, [x[start:start + count]])[gshard.outputs[0]]
+        # ... and the slices land in one buffer at the offsets the rule gives (all_gather stands in for the host buffer here)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (start, out))
+        # the barrier protocol of bench.py: three barriers, only rank 0 works between them
+        for _ in range(3):
+            dist.barrier()
+        q.put((rank, gathered))
     finally:
         dist.destroy_process_group()
 
 
-def test_world_size_2_gloo_sharding_broadcast_and_timing(oracle):
+def test_world_size_2_gloo_slices_equal_the_whole_batch(oracle):
     import torch.multiprocessing as mp
 
     world = 2
@@ -75,11 +77,11 @@ def test_world_size_2_gloo_sharding_broadcast_and_timing(oracle):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert all(r[1] for r in res), "weight arena differs after the broadcast"
-    assert res[0][4] == [11.0, 5.0] and res[1][4] == [11.0, 5.0]
-    # shards merged in rank order == the whole batch in one run
     gfull, b = workloads.tiny_net(abi.DT_INT8, batch=5, seed=3)
     x = b.random_input(11)
     want = oracle.run(gfull, [x])[gfull.outputs[0]]
-    got = sharding.merge_shards([r[3] for r in res])
-    assert np.array_equal(got, want)
+    for rank, gathered in res:
+        got = np.zeros_like(want)
+        for start, out in gathered:
+            got[start:start + out.shape[0]] = out
+        assert np.array_equal(got, want), rank
