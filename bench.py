@@ -94,16 +94,19 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic(workload, batch, family):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel family, summed over its launches of one step, from the
-    committed `ncu --set full` capture (profiles/r01_ncu_traffic.json; not measured live: ncu replays every kernel ~40x).
-    None when the capture is of another workload / batch."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    if d.get("workload") != workload or d.get("batch") != batch:
-        return None
-    f = d["families"].get(family)
-    return float(f["dram_bytes_per_step"]) if f else None
+    committed `ncu --set full` capture (profiles/rNN_ncu_traffic.json, newest round first, made by tools/ncu_traffic_json.py; not
+    measured live: ncu replays every kernel ~40x).  None when no capture is of this workload / batch."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        d = json.load(open(p))
+        if d.get("workload") != workload or d.get("batch") != batch:
+            continue
+        f = d["families"].get(family)
+        if f:
+            return float(f["dram_bytes_per_step"])
+    return None
 
 
 def build_workload(name, batch):

@@ -150,7 +150,9 @@ static __device__ __noinline__ int requant(int32_t acc, int oc, const EpiParams&
 // ALU-pipe instructions per element: 3.0 (was 5.75 with scalar FMNMX clamps and per-element guards).
 #define TB200_MAGIC 12582912.0f       // 1.5 * 2^23
 #define TB200_MAGIC_BITS 0x4B400000   // its bit pattern: as_float(MAGIC_BITS + i) == MAGIC + i for |i| < 2^22
+#ifndef TB200_TIE_EPS // (tools/build_nofix_lib.sh overrides it to measure what the rare path costs; never in the product build)
 #define TB200_TIE_EPS 1.220703125e-4f // 2^-13
+#endif
 
 // ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2) ----
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
@@ -306,6 +308,32 @@ __device__ __noinline__ uint32_t requant_fix_word(uint32_t word, int32_t a0, int
         if (fabsf(d) > 0.5f - TB200_TIE_EPS)
         {
             const uint32_t q = (uint32_t)requant(a[j], oc0 + j, e) & 0xffu;
+            word = (word & ~(0xffu << (8 * j))) | (q << (8 * j));
+        }
+    }
+    return word;
+}
+
+// The same for the uint8 tensor-core layers, whose fast epilogue has the int8 form t = fl((float)a * M) with a = true accumulator +
+// y[oc] (y: integer constant of the channel INCLUDING the bias, FastPar4 {M, M, y, y}): `a` are those sums.  Only the elements that
+// really sit in the guard band go through the literal arithmetic (which wants the accumulator without the bias).  One call per
+// guarded word: the four candidates are examined together, so the rare path costs one parameter load and usually one literal
+// requantisation -- an epilogue warp that lingers here holds up its whole accumulator stage.
+static __device__ __noinline__ uint32_t requant_fix_word_u8(uint32_t word, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int oc0, int oc_limit, const EpiParams& e)
+{
+    const FastPar4 f = fast_par4_ldg(e, oc0);
+    const int32_t a[4] = {a0, a1, a2, a3};
+    const float m[4] = {f.a.x, f.a.y, f.b.x, f.b.y};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float t = __fmul_rn((float)a[j], m[j]);
+        const float r = __fadd_rn(t, TB200_MAGIC);
+        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
+        if (fabsf(d) > 0.5f - TB200_TIE_EPS && oc0 + j < oc_limit)
+        {
+            const int32_t b = e.has_bias ? __ldg(e.bias + oc0 + j) : 0;
+            const uint32_t q = (uint32_t)requant(a[j] - b, oc0 + j, e) & 0xffu;
             word = (word & ~(0xffu << (8 * j))) | (q << (8 * j));
         }
     }

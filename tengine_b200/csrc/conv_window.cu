@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
             {
                 if (NCHW)
                 {
-                    for (int i = tid; i < a.in_bytes; i += 128)
+                    // one thread per window row (C * box_h of them); only the columns the gather reads: [xoff, xoff + 15*S + K)
+                    const int x_lo = a.xoff, x_hi = a.xoff + 15 * a.stride + KHW;
+                    for (int row = tid; row < a.c * a.box_h; row += 128)
                     {
-                        const int x = i % a.box_w, y = (i / a.box_w) % a.box_h;
-                        if (iy0 + y < 0 || iy0 + y >= a.h || ix0 + x < 0 || ix0 + x >= a.w_in)
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(win + (uint32_t)i), "r"(a.fill & 0xffu) : "memory");
+                        const int y = row % a.box_h;
+                        const bool row_oob = iy0 + y < 0 || iy0 + y >= a.h;
+                        const uint32_t rp = win + (uint32_t)(row * a.box_w);
+                        for (int x = x_lo; x < x_hi; x++)
+                            if (row_oob || ix0 + x < 0 || ix0 + x >= a.w_in) asm volatile("st.shared.u8 [%0], %1;" ::"r"(rp + (uint32_t)x), "r"(a.fill & 0xffu) : "memory");
                     }
                 }
                 else
@@ -151,7 +155,10 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
             uint32_t row[NW];
 #pragma unroll
             for (int j = 0; j < NW; j++) row[j] = 0;
-            const uint32_t base = win + (uint32_t)((th * a.stride) * a.box_w + tw * a.stride + a.xoff);
+            // row bases advance by box_w (and by the rest of the plane between channels): the 27 / 147 byte loads then carry
+            // immediate offsets 0..K-1 instead of one IMAD each
+            uint32_t rb = win + (uint32_t)((th * a.stride) * a.box_w + tw * a.stride + a.xoff);
+            const uint32_t plane_skip = (uint32_t)((a.box_h - KHW) * a.box_w);
 #pragma unroll
             for (int c = 0; c < 3; c++)
             {
@@ -159,14 +166,18 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
                 {
 #pragma unroll
                     for (int kh = 0; kh < KHW; kh++)
+                    {
 #pragma unroll
                         for (int kw = 0; kw < KHW; kw++)
                         {
                             uint32_t b;
-                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(base + (uint32_t)((c * a.box_h + kh) * a.box_w + kw)));
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(rb + (uint32_t)kw)); // rb + constant: folds into the load's immediate
                             const int k = (c * KHW + kh) * KHW + kw; // compile-time after unrolling
                             row[k >> 2] += b << (8 * (k & 3));       // disjoint bytes: add == or (IMAD, off the ALU pipe)
                         }
+                        rb += (uint32_t)a.box_w;
+                    }
+                    rb += plane_skip;
                 }
             }
             if (U8)
@@ -264,14 +275,14 @@ __global__ void __launch_bounds__(128) conv_window_tc_kernel(const __grid_consta
                         for (int j = 0; j < 4; j++)
                             if (gw[j] > 0.5f - TB200_TIE_EPS)
                             {
+                                int32_t at[4]; // accumulator + y of the word's four channels (what the fast path multiplied by M)
 #pragma unroll
                                 for (int t = 0; t < 4; t++)
                                 {
-                                    const int oc = c + j * 4 + t;
                                     const float4 pp = lds_f4(sPar + c * 8 + ((j * 4 + t) >> 1) * 16);
-                                    const int32_t acc = (int32_t)v[j * 4 + t] + rowc + __float_as_int((t & 1) ? pp.w : pp.z) - (e.has_bias ? __ldg(e.bias + oc) : 0);
-                                    if (oc < a.oc) w[j] = requant_fix_byte(w[j], t, acc, oc, e);
+                                    at[t] = (int32_t)v[j * 4 + t] + rowc + __float_as_int((t & 1) ? pp.w : pp.z);
                                 }
+                                w[j] = requant_fix_word_u8(w[j], at[0], at[1], at[2], at[3], c + j * 4, a.oc, e);
                             }
                     }
                     if (c + 16 > a.oc)
@@ -392,12 +403,12 @@ cudaError_t launch_conv_window(const WindowPlan& p, const void* w, void* out, co
 #define TB200_WIN_CASE(MD, U, LY)                                                                                                           \
     if (mode == MD && (e.is_uint8 != 0) == U && p.layout == LY)                                                                             \
     {                                                                                                                                       \
-        static bool attr = false;                                                                                                           \
-        if (!attr)                                                                                                                          \
+        static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                                           \
+        if (!attr_dev[current_device() & 63])                                                                                                                          \
         {                                                                                                                                   \
             cudaError_t err = cudaFuncSetAttribute(conv_window_tc_kernel<MD, U, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
             if (err != cudaSuccess) return err;                                                                                             \
-            attr = true;                                                                                                                    \
+            attr_dev[current_device() & 63] = true;                                                                                                                    \
         }                                                                                                                                   \
         conv_window_tc_kernel<MD, U, LY><<<grid, 128, (size_t)p.smem_bytes, st>>>(tm, a, e);                                                \
         return cudaGetLastError();                                                                                                          \

@@ -25,7 +25,8 @@
 
 using namespace tb200;
 
-#define TB200_OP_NOP_ (-1) // planner-internal: a node folded into its producer
+#define TB200_OP_NOP_ (-1)  // planner-internal: a node folded into its producer
+#define TB200_OP_LUT2_ (-2) // planner-internal: Sigmoid + Eltwise-PROD with the Sigmoid's input, as one byte table
 #define TB200_PACK_FORMAT 3  // bump whenever the layout of the packed weight arena changes (pack cache key)
 
 // ---- packed-weight cache directory: tb200_pack_cache_dir() or the environment ----
@@ -434,7 +435,7 @@ static EpiParams make_epi(const tb200_layer_desc& L, const tb200_tensor_desc& ti
 static size_t gemm_weight_bytes(int ocp, int k, bool u8)
 {
     const int bn = gemm_block_n(ocp, u8), nt = (ocp + bn - 1) / bn;
-    return (size_t)nt * bn * k;
+    return (size_t)nt * (bn + (u8 ? 16 : 0)) * k;
 }
 
 struct WeightBlob
@@ -535,6 +536,26 @@ static void build_byte_lut(int op, bool u8, const tb200_tensor_desc& tin, const 
     }
 }
 
+// Eltwise (SUM / PROD) of two bytes with the arithmetic of eltwise/eltwise_ref.c:311-583 (uint8), 585-845 (int8) -- the statements of
+// kernels_direct.cu pointwise_exact_byte -- for tables of node pairs whose two operands are functions of the same byte.
+static uint8_t eltwise_byte(bool u8, int elt_type, int a, const tb200_tensor_desc& ta, int b, const tb200_tensor_desc& tb, const tb200_tensor_desc& to)
+{
+    volatile float f0, f1;
+    if (u8) f0 = (float)(a - ta.zero_point) * ta.scale, f1 = (float)(b - tb.zero_point) * tb.scale;
+    else f0 = (float)(int)(int8_t)a * ta.scale, f1 = (float)(int)(int8_t)b * tb.scale;
+    volatile float f = (elt_type == TB200_ELT_SUM) ? f0 + f1 : f0 * f1;
+    volatile float t = f / to.scale;
+    int q = (int)roundf(t);
+    if (u8)
+    {
+        q += to.zero_point;
+        q = q > 255 ? 255 : (q < 0 ? 0 : q);
+    }
+    else
+        q = q > 127 ? 127 : (q < -127 ? -127 : q);
+    return (uint8_t)(q & 0xff);
+}
+
 // (leaky) ReLU as a byte table, with the arithmetic of relu/relu_kernel_ref_int8.c:41-94 and relu_kernel_ref_uint8.c:41-96 (the same
 // statements as kernels_direct.cu pointwise_exact_byte): used where the node is folded into the max pooling that follows it.
 static void build_relu_lut(bool u8, const tb200_tensor_desc& tin, const tb200_tensor_desc& tout, float slope, uint8_t* lut)
@@ -572,6 +593,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
     //      result has no other reader: the ReLU is then max(byte, zero point) on the requantised bytes (relu_same_scale_kernel),
     //      applied inside the eltwise kernel -- one pass over memory instead of two, the intermediate tensor is never stored.
     //      Not under TB200_PRERUN_NO_GRAPH, whose contract is that every intermediate stays readable. ----
+    const std::vector<tb200_layer_desc> src_layers(layers, layers + num_layers); // the descriptors as the caller gave them
     std::vector<tb200_layer_desc> fused(layers, layers + num_layers);
     std::vector<int> post_relu(num_layers, 0);
     if (!(flags & TB200_PRERUN_NO_GRAPH) && !getenv("TB200_NO_FUSION"))
@@ -625,6 +647,34 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             if (tr.scale != tp.scale || tr.zero_point != tp.zero_point || tr.data_type != tp.data_type) continue;
             pool_relu[lj] = li;
             fused[lj].inputs[0] = R.inputs[0]; // the pooling reads what the ReLU read
+            fused[li].op = TB200_OP_NOP_, fused[li].num_inputs = 0;
+        }
+    }
+    // Sigmoid -> Eltwise-PROD with the Sigmoid's own input (x * sigmoid(x): how an int8 YOLOv5s spells SiLU): both
+    // operands of the product are functions of the same byte of x, so the PAIR is one byte table -- sigmoid's table composed with
+    // the reference's eltwise arithmetic, built at prerun -- and one pass (1 read, 1 write) replaces two (3 reads, 2 writes).
+    std::vector<int> silu_sig(num_layers, -1); // [eltwise layer] = the folded Sigmoid layer
+    if (!(flags & TB200_PRERUN_NO_GRAPH) && !getenv("TB200_NO_FUSION"))
+    {
+        std::vector<int> readers(num_tensors, 0), reader_layer(num_tensors, -1);
+        for (int li = 0; li < num_layers; li++)
+            for (int k = 0; k < fused[li].num_inputs && k < 4; k++)
+                if (fused[li].inputs[k] >= 0 && fused[li].inputs[k] < num_tensors) readers[fused[li].inputs[k]]++, reader_layer[fused[li].inputs[k]] = li;
+        std::vector<char> is_out(num_tensors, 0);
+        for (int i = 0; i < num_outputs; i++)
+            if (output_ids[i] >= 0 && output_ids[i] < num_tensors) is_out[output_ids[i]] = 1;
+        for (int li = 0; li < num_layers; li++)
+        {
+            const tb200_layer_desc& S = fused[li];
+            if (S.op != TB200_OP_SIGMOID || S.output < 0 || S.output >= num_tensors || readers[S.output] != 1 || is_out[S.output]) continue;
+            const int lj = reader_layer[S.output];
+            const tb200_layer_desc& E = fused[lj];
+            if (lj <= li || E.op != TB200_OP_ELTWISE || E.elt_type != TB200_ELT_PROD || E.num_inputs != 2 || post_relu[lj]) continue;
+            const int other = E.inputs[0] == S.output ? E.inputs[1] : (E.inputs[1] == S.output ? E.inputs[0] : -1);
+            if (other != S.inputs[0]) continue;
+            silu_sig[lj] = li;
+            fused[lj].op = TB200_OP_LUT2_, fused[lj].num_inputs = 1, fused[lj].inputs[0] = S.inputs[0];
+            fused[lj].axis = (E.inputs[0] == S.output) ? 0 : 1; // which operand of the product was the sigmoid (operand scales differ)
             fused[li].op = TB200_OP_NOP_, fused[li].num_inputs = 0;
         }
     }
@@ -757,6 +807,8 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             kind[li] = K_UPSAMPLE;
         else if (L.op == TB200_OP_IDENTITY)
             kind[li] = K_COPY;
+        else if (L.op == TB200_OP_LUT2_)
+            kind[li] = K_LUT;
         else if (L.op == TB200_OP_SIGMOID || L.op == TB200_OP_HARDSWISH)
         {
             // the reference has no int8 hardswish (hardswish_ref.c:59-66): nothing to be identical to
@@ -994,7 +1046,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     const uint8_t* b = (const uint8_t*)p;
                     for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
                 };
-                const int ver = TB200_PACK_FORMAT;
+                const int ver = TB200_PACK_FORMAT * 16 + gemm_sx_mode();
                 mix(&ver, sizeof ver), mix(&g->w_bytes, sizeof g->w_bytes), mix(&num_layers, sizeof num_layers);
                 for (int li = 0; li < num_layers; li++)
                 {
@@ -1072,6 +1124,20 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                                layers[pool_relu[li]].negative_slope, img.data() + blobs[li].w_off);
                 continue;
             }
+            if (kind[li] == K_LUT && L.op == TB200_OP_LUT2_)
+            {
+                // x -> sigmoid(x) (its own requantisation, the Sigmoid node's output tensor) -> eltwise product with x
+                const tb200_layer_desc& S = src_layers[silu_sig[li]];
+                const tb200_layer_desc& E = src_layers[li];
+                const tb200_tensor_desc &tx = tensors[S.inputs[0]], &ts = tensors[S.output], &to = tensors[E.output];
+                const bool u8l = tx.data_type == TB200_DT_UINT8;
+                uint8_t sig[256];
+                build_byte_lut(TB200_OP_SIGMOID, u8l, tx, ts, sig);
+                uint8_t* lut = img.data() + blobs[li].w_off;
+                for (int b = 0; b < 256; b++)
+                    lut[b] = (E.inputs[0] == S.output) ? eltwise_byte(u8l, TB200_ELT_PROD, sig[b], ts, b, tx, to) : eltwise_byte(u8l, TB200_ELT_PROD, b, tx, sig[b], ts, to);
+                continue;
+            }
             if (kind[li] == K_LUT)
             {
                 build_byte_lut(L.op, g->tensors[L.inputs[0]].d.data_type == TB200_DT_UINT8, g->tensors[L.inputs[0]].d, g->tensors[L.output].d,
@@ -1087,7 +1153,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
             uint8_t* dst = img.data() + blobs[li].w_off;
             const bool tc = kind[li] == K_GEMM || kind[li] == K_IGEMM;
             // row of output channel o in the packed B operand (uint8 tensor-core tiles carry 16 extra rows each)
-            const int bn = tc ? gemm_block_n(tout.cp, u8) : tout.cp, bnx = bn;
+            const int bn = tc ? gemm_block_n(tout.cp, u8) : tout.cp, bnx = tc ? gemm_tile_rows(tout.cp, u8 ? 1 + L.weight_zero : 0) : bn;
             auto brow = [&](int o) -> size_t { return (size_t)(o / bn) * bnx + (o % bn); };
             size_t krow = 0; // K extent of one packed row
             if (L.op == TB200_OP_FC)
@@ -1154,6 +1220,8 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                         }
                     }
                 }
+                if (bnx != bn) // sum(x) of every pixel from the main MMA: 16 rows of ones close every B tile (gemm_tcgen05.cu, sx_mode 0)
+                    for (int tile = 0; tile * bn < tout.cp; tile++) memset(dst + ((size_t)tile * bnx + bn) * krow, 1, (size_t)16 * krow);
                 const int taps = L.op == TB200_OP_FC ? 1 : L.kernel_h * L.kernel_w;
                 const int kk = L.op == TB200_OP_FC ? C * H * W : C; // real K elements per tap
                 std::vector<int64_t> tapc((size_t)taps * OC, 0); // what a tap that falls into the padding must give back: zx*(sum_c w - Cin*zw)

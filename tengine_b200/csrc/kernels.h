@@ -129,7 +129,16 @@ struct GemmPlan
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.
+// ordinal of the calling thread's current CUDA device (launchers keep per-device state: cudaFuncSetAttribute is per device)
+static inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
 int gemm_block_n(int ocp, int u8);
+int gemm_sx_mode();                  // TB200_U8_SX: where the uint8 path's sum(x) comes from (gemm_tcgen05.cu)
+int gemm_tile_rows(int ocp, int u8); // rows of one packed B tile (u8 = 1 + weight zero point, 0 for int8)
 int gemm_plan_create(GemmPlan* plan, const void* a, long long lda, const void* b, void* out, long long m, int k, int oc, int ocp, int ldo,
                      int variant, int u8);
 int gemm_plan_create_conv(GemmPlan* plan, const void* in, const void* w, void* out, const ConvShape& s, int u8);

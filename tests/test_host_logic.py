@@ -37,7 +37,8 @@ def test_bench_traffic_comes_from_the_committed_capture():
     sys.path.insert(0, ROOT)
     import bench
 
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    newest = [n for n in ("r02_ncu_traffic.json", "r01_ncu_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", n))][0]
+    d = json.load(open(os.path.join(ROOT, "profiles", newest)))
     fam = next(iter(d["families"]))
     assert bench.ncu_traffic(d["workload"], d["batch"], fam) == pytest.approx(d["families"][fam]["dram_bytes_per_step"])
     assert bench.ncu_traffic(d["workload"], d["batch"] + 1, fam) is None  # another batch: no claim
