@@ -77,7 +77,9 @@ struct tb200_context
     const char* bcast_kind = "none";
     std::vector<HostReg> host_regs;
     std::vector<const void*> host_reg_failed;
+    void* fixq = nullptr; // scratch of the GEMM kernels' deferred rare path: FIXQ_CAP entries per SM (gemm_tcgen05.cu)
 };
+static constexpr int FIXQ_CAP = 4096;
 
 // ---- NCCL, loaded at run time (libnccl.so.2: the copy torch already mapped when running under Python, the system one
 //      otherwise) so that single-GPU users never need it.  Only what the one broadcast at prerun needs. ----
@@ -257,6 +259,8 @@ static int context_create_one(int cuda_device, tb200_context** out)
     c->device = cuda_device;
     c->num_sms = sms;
     c->stream = st;
+    static const bool no_fixq = getenv("TB200_NO_FIXQ") != nullptr; // A/B switch: guarded elements fixed inline
+    if (!no_fixq) CUDA_OK(cudaMalloc(&c->fixq, (size_t)sms * FIXQ_CAP * 16));
     *out = c;
     return 0;
 }
@@ -329,6 +333,7 @@ int tb200_context_destroy(tb200_context* ctx)
     for (tb200_context* p : ctx->peers) tb200_context_destroy(p);
     cudaSetDevice(ctx->device);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->fixq) cudaFree(ctx->fixq);
     delete ctx;
     return 0;
 }
@@ -1492,6 +1497,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                 {
                     int rc = gemm_plan_create_conv(&s.gemm, s.in, s.w, s.out, s.cs, u8 ? 1 + L.weight_zero : 0);
                     if (rc) return bail(fail(rc, "layer %d: implicit-GEMM plan failed", li));
+                    s.gemm.fixq = ctx->fixq, s.gemm.fixq_cap = FIXQ_CAP;
                 }
                 if (s.kind == K_GEMM)
                 {
@@ -1499,6 +1505,7 @@ static int prerun_one(tb200_context* ctx, const tb200_tensor_desc* tensors, int 
                     const int kdim = fc ? H * W * tin.cp : tin.cp;
                     int rc = gemm_plan_create(&s.gemm, s.in, kdim, s.w, s.out, m, kdim, OC, tout.cp, tout.cp, 0, u8 ? 1 + L.weight_zero : 0);
                     if (rc) return bail(fail(rc, "layer %d: TMA descriptor creation failed (m=%lld k=%d oc=%d)", li, m, kdim, OC));
+                    s.gemm.fixq = ctx->fixq, s.gemm.fixq_cap = FIXQ_CAP;
                 }
             }
             else if (L.op == TB200_OP_POOL)

@@ -79,6 +79,12 @@ struct GemmArgs
     int par_all;     // the constants of every channel are resident (loaded once); else reloaded per N tile
     int b_res;       // the N tile's weights (all k-blocks) are loaded once and stay in smem; the ring carries A only
     int teams;       // the epilogue warps form two teams, one per accumulator stage (see the epilogue)
+    // deferred rare path: a guarded element is queued {m-tile, row, channel, accumulator} and recomputed literally by all threads of the
+    // CTA after its last tile, instead of holding up its epilogue warp (and with it the accumulator stage); null = inline
+    uint4* fixq;
+    int fixq_cap; // entries per CTA
+    uint8_t* out_base;
+    int ldo, m_rows; // output row pitch in bytes; rows of the flat GEMM
     const int32_t* btab; // uint8 convolutions: [border pattern][OCp] summed corrections of the taps a border pixel misses (engine.cu)
     unsigned long long* trace; // debug (TB200_GEMM_TRACE): event timeline of CTA 0, see gemm_trace_report
 };
@@ -104,9 +110,93 @@ struct __align__(16) GemmSmemCtl
 
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
+// ---- the rare path of the fast epilogue, deferred -----------------------------------------------------------------------------
+// An element whose t sits inside the tie guard needs the literal reference arithmetic (common.cuh requant(): divisions, per-channel
+// loads, every recipe).  Done inline it occupies ONE lane of an epilogue warp for hundreds of cycles while the other fifteen warps
+// finish their groups and then wait for it at the accumulator hand-over: with ~7 guarded words per 128 x 256 stage this was 16-20 %
+// of the GEMM time (profiles/r02_rare_path.txt).  Instead the lane appends {m-tile, row, channel, accumulator} to the CTA's queue in
+// global memory (L2) and carries on with the fast byte; after the CTA's last tile all 512 epilogue threads recompute the queued
+// elements in parallel and patch the bytes in the output tensor (the tile's TMA store has completed by then).  A full or absent
+// queue falls back to the inline computation, so the result never depends on the queue.
+// (queue state in static shared memory, so that the rare-path functions need no extra arguments: passing the kernel arguments and a
+//  counter pointer through the epilogue's inner loop cost registers there and made the int8 kernel 12 % slower)
+struct FixQueue
+{
+    uint4* q;       // this CTA's segment, null = fix inline
+    uint32_t cap;   // entries in the segment
+    uint32_t count; // elements queued so far (may exceed cap: the surplus was fixed inline)
+};
+__shared__ FixQueue s_fixq;
+
+__device__ __forceinline__ bool fixq_push(uint32_t mtile, int oc, int32_t acc)
+{
+    if (!s_fixq.q) return false;
+    const uint32_t slot = atomicAdd(&s_fixq.count, 1u);
+    if (slot >= s_fixq.cap) return false;
+    const uint32_t row = ((threadIdx.x >> 5) & 3u) * 32u + (threadIdx.x & 31u); // TMEM lane of this thread = row of the m-tile
+    s_fixq.q[slot] = make_uint4(mtile, row | ((uint32_t)oc << 8), (uint32_t)acc, 0u);
+    return true;
+}
+
+// One guarded word (final fast bytes in `word`): find the elements that really sit in the band, queue them (or fix them here).
+// a[j]: what the fast path converted to float -- int8: the raw accumulator (y is added inside), uint8: accumulator + sum(x) term + y.
+template <bool U8, bool FUSE>
+__device__ __noinline__ uint32_t gemm_fix_word(uint32_t word, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int oc0, int oc_limit, uint32_t mtile,
+                                               const EpiParams& e)
+{
+    const FastPar4 f = fast_par4_ldg(e, oc0);
+    const int32_t a[4] = {a0, a1, a2, a3};
+    const float m[4] = {f.a.x, f.a.y, f.b.x, f.b.y}, y[4] = {f.a.z, f.a.w, f.b.z, f.b.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float t = U8 ? __fmul_rn((float)a[j], m[j]) : (FUSE ? __fmaf_rn((float)a[j], m[j], y[j]) : __fmul_rn((float)(a[j] + __float_as_int(y[j])), m[j]));
+        const float r = __fadd_rn(t, TB200_MAGIC);
+        const float d = __fsub_rn(t, __fsub_rn(r, TB200_MAGIC));
+        if (fabsf(d) > 0.5f - TB200_TIE_EPS && oc0 + j < oc_limit)
+        {
+            if (!fixq_push(mtile, oc0 + j, a[j]))
+            {
+                // the literal arithmetic wants the accumulator without the bias (uint8: y holds it)
+                const int32_t acc = a[j] - ((U8 && e.has_bias) ? __ldg(e.bias + oc0 + j) : 0);
+                const uint32_t q = (uint32_t)requant(acc, oc0 + j, e) & 0xffu;
+                word = (word & ~(0xffu << (8 * j))) | (q << (8 * j));
+            }
+        }
+    }
+    return word;
+}
+
+// After the CTA's last tile (every epilogue warp has waited for its own bulk stores): recompute the queued elements, one per thread.
+template <bool U8>
+__device__ __forceinline__ void fixq_drain(const GemmArgs& g, const EpiParams& e)
+{
+    const uint32_t n = s_fixq.count < s_fixq.cap ? s_fixq.count : s_fixq.cap;
+    for (uint32_t k = threadIdx.x; k < n; k += EPI_THREADS)
+    {
+        const uint4 q = s_fixq.q[k];
+        const int mt = (int)q.x, r = (int)(q.y & 127u), oc = (int)(q.y >> 8);
+        long long pix;
+        bool ok = r < g.rows_valid;
+        if (!g.conv)
+            pix = (long long)mt * BLOCK_M + r, ok = ok && pix < g.m_rows;
+        else
+        {
+            int cn0, coh0, cow0;
+            tile_origin(g, mt, cn0, coh0, cow0);
+            if (g.out_mode == 0) pix = (long long)cn0 * g.oh * g.ow + r, ok = ok && pix < (long long)g.nimg * g.oh * g.ow;
+            else if (g.out_mode == 1) pix = (long long)cn0 * g.oh * g.ow + coh0 * g.ow + r, ok = ok && coh0 * g.ow + r < g.oh * g.ow;
+            else pix = ((long long)cn0 * g.oh + coh0) * g.ow + cow0 + r, ok = ok && cow0 + r < g.ow;
+        }
+        if (!ok || oc >= g.oc) continue; // a row the TMA store clipped
+        const int32_t acc = (int32_t)q.z - ((U8 && e.has_bias) ? __ldg(e.bias + oc) : 0);
+        g.out_base[(size_t)pix * g.ldo + oc] = (uint8_t)requant(acc, oc, e);
+    }
+}
+
 // 16 accumulator columns of one row -> 16 output bytes into the warp's staging buffer (int8, fast path).
 template <bool FUSE>
-__device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, int oc0, const EpiParams& e)
+__device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint32_t par_addr, uint32_t dst_addr, int oc0, uint32_t mtile, const EpiParams& e)
 {
     uint32_t w[4];
     float gw[4];
@@ -131,7 +221,7 @@ __device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (gw[j] > 0.5f - TB200_TIE_EPS)
-                w[j] = requant_fix_word<FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, e);
+                w[j] = gemm_fix_word<false, FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, 0x7fffffff /* pad channels have M = y = 0: never guarded */, mtile, e);
     }
     sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
@@ -160,7 +250,7 @@ __device__ __forceinline__ void epilogue_unit_exact(const uint32_t (&v)[16], uin
 
 template <bool EXACT, bool BORDER>
 __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_t rowc, uint32_t pad_mask_in, const GemmArgs& g, uint32_t par_addr,
-                                                 uint32_t dst_addr, int oc0, const EpiParams& e)
+                                                 uint32_t dst_addr, int oc0, uint32_t mtile, const EpiParams& e)
 {
     const uint32_t pad_mask = BORDER ? pad_mask_in : 0u; // BORDER == false (1x1 / FC, unpadded convs): the correction code compiles away
     uint32_t w[4];
@@ -210,7 +300,7 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
                         const int4 c = __ldg(reinterpret_cast<const int4*>(g.btab + (size_t)pad_mask * g.ocp + oc0 + j * 4));
                         a[0] += c.x, a[1] += c.y, a[2] += c.z, a[3] += c.w;
                     }
-                    w[j] = requant_fix_word_u8(w[j], a[0], a[1], a[2], a[3], oc0 + j * 4, g.oc, e);
+                    w[j] = gemm_fix_word<true, false>(w[j], a[0], a[1], a[2], a[3], oc0 + j * 4, g.oc, mtile, e);
                 }
         }
         if (oc0 + 16 > g.oc)
@@ -304,6 +394,7 @@ __global__ void __launch_bounds__(U8 ? GEMM_THREADS_U8 : GEMM_THREADS, 1)
         for (int s = 0; s < g.stages; s++) mbar_init(&ctl->full[s], 1), mbar_init(&ctl->empty[s], 1 + sumw);
         for (int s = 0; s < 2; s++) mbar_init(&ctl->tmem_full[s], 1 + sumw), mbar_init(&ctl->tmem_empty[s], g.teams ? EPI_WARPS / 2 : EPI_WARPS);
         mbar_init(&ctl->b_full, 1);
+        s_fixq.q = g.fixq ? g.fixq + (size_t)blockIdx.x * g.fixq_cap : nullptr, s_fixq.cap = (uint32_t)g.fixq_cap, s_fixq.count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0)
@@ -583,9 +674,9 @@ __global__ void __launch_bounds__(U8 ? GEMM_THREADS_U8 : GEMM_THREADS, 1)
                     {
                         const int c = cg0 + half * 64 + k * 16;
                         const uint32_t dst = sdst + (((uint32_t)(half * 4 + k) << 4) ^ xl);
-                        if (U8) epilogue_unit_u8<MODE == 2, BORDER>(v, rowc, pad, g, par_s + c * 8, dst, n0 + c, e);
+                        if (U8) epilogue_unit_u8<MODE == 2, BORDER>(v, rowc, pad, g, par_s + c * 8, dst, n0 + c, (uint32_t)(mt0 + i), e);
                         else if (MODE == 2) epilogue_unit_exact(v, dst, n0 + c, g.oc, e);
-                        else epilogue_unit_fast<MODE == 1>(v, par_s + c * 8, dst, n0 + c, e);
+                        else epilogue_unit_fast<MODE == 1>(v, par_s + c * 8, dst, n0 + c, (uint32_t)(mt0 + i), e);
                     };
                     if (CS == 1)
                     {
@@ -638,6 +729,13 @@ __global__ void __launch_bounds__(U8 ? GEMM_THREADS_U8 : GEMM_THREADS, 1)
             if (++as == 2) as = 0, aphase ^= 1;
         }
         if (lane == 0) bulk_wait<0>(); // all of this warp's stores have completed
+        if (g.fixq && MODE != 2)
+        {
+            // deferred rare path: every warp's stores are complete (and its queue entries written) once all have passed this barrier
+            __threadfence_block();
+            epilogue_bar_sync();
+            fixq_drain<U8>(g, e);
+        }
     }
 
     tcgen05_fence_before();
@@ -1548,7 +1646,7 @@ int gemm_plan_create(GemmPlan* p, const void* a, long long lda, const void* b, v
 {
     if (m <= 0 || k <= 0 || (k & 15) || (ocp & 15) || (lda & 15) || (ldo & 15)) return TB200_ERR_INVALID;
     memset(p, 0, sizeof *p);
-    p->m = m, p->k = k, p->oc = oc, p->ocp = ocp, p->ldo = ldo, p->variant = variant;
+    p->m = m, p->k = k, p->oc = oc, p->ocp = ocp, p->ldo = ldo, p->variant = variant, p->out = out;
     p->block_k = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     p->swizzle = p->block_k;
     p->k_blocks = (k + p->block_k - 1) / p->block_k;
@@ -1605,7 +1703,7 @@ int gemm_plan_create_conv(GemmPlan* p, const void* in, const void* w, void* out,
     if (taps > 1 && (s.cp % 32)) return TB200_ERR_UNSUPPORTED; // a k-block must not straddle two taps
     memset(p, 0, sizeof *p);
     p->conv = 1;
-    p->m = (long long)s.n * s.oh * s.ow, p->oc = s.oc, p->ocp = s.ocp, p->ldo = s.ocp, p->variant = 0;
+    p->m = (long long)s.n * s.oh * s.ow, p->oc = s.oc, p->ocp = s.ocp, p->ldo = s.ocp, p->variant = 0, p->out = out;
     if (taps == 1) p->block_k = s.cp <= 32 ? 32 : (s.cp <= 64 ? 64 : 128);
     else p->block_k = (s.cp % 128 == 0) ? 128 : ((s.cp % 64 == 0) ? 64 : 32);
     p->swizzle = p->block_k;
@@ -1752,6 +1850,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
     g.a_tx_bytes = p.a_tx_bytes;
     g.u8 = p.u8, g.bnx = p.bnx, g.taps = p.taps, g.in_h = p.in_h, g.in_w = p.in_w, g.btab = btab, g.b_signed = p.b_signed, g.cplane = p.cplane;
     g.sx_mode = !p.cplane ? -1 : (p.bnx != p.block_n ? 0 : 3);
+    g.fixq = (uint4*)p.fixq, g.fixq_cap = p.fixq_cap, g.out_base = (uint8_t*)p.out, g.ldo = p.ldo, g.m_rows = (int)p.m;
     g.tcols = p.bnx;
     g.mt = p.mt;
     g.num_super = (int)(((p.m_tiles + p.mt - 1) / p.mt) * p.n_tiles);
@@ -1798,7 +1897,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
         static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                              \
         if (!attr_dev[current_device() & 63])                                                                                                             \
         {                                                                                                                      \
-            err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (err != cudaSuccess) return err;                                                                                \
             attr_dev[current_device() & 63] = true;                                                                                                       \
         }                                                                                                                      \

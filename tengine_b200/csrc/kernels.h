@@ -126,6 +126,9 @@ struct GemmPlan
     alignas(64) unsigned char tmap_b_s[128];
     int simple, s_block_n, s_n_tiles, s_smem;
     void* out;
+    // deferred rare path (gemm_tcgen05.cu fixq_*): per-context scratch of fixq_cap 16-byte entries per CTA; null = fix inline
+    void* fixq;
+    int fixq_cap;
     int variant; // debug: descriptor variant selector (0 = default)
 };
 // Build TMA descriptors for fixed device pointers. Returns 0 or a negative TB200_ERR_*.

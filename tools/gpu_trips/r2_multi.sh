@@ -4,9 +4,11 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/multi_gpus.txt 2>&1
+if [ "$2" != notest ]; then
 timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_tengine_integration.py -m gpu -q -p no:cacheprovider --timeout 600 > gpurun_out/pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_multi_${N}gpu.log
 grep -E "passed|failed|skipped" gpurun_out/pytest_multi_${N}gpu.log | tail -2; grep -E "^FAILED|^ERROR" gpurun_out/pytest_multi_${N}gpu.log | head
-NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_mobilenet_${N}gpu.log 2>&1
+fi
+NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --cpu-window 0 > gpurun_out/bench_mobilenet_${N}gpu.log 2>&1
 tail -n 1 gpurun_out/bench_mobilenet_${N}gpu.log | cut -c1-1200
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --workload yolov3_tiny_uint8 --global-batch 128 > gpurun_out/bench_yolo_strong_${N}gpu.log 2>&1
 tail -n 1 gpurun_out/bench_yolo_strong_${N}gpu.log | cut -c1-1200
