@@ -13,8 +13,8 @@ through tb200_graph_*) over one synthetic batch of 256 images per GPU.
 Multi-GPU: ONE process drives all N GPUs through the product (a tb200 context over N GPUs): every step hands ONE batch of
 256 x N images (weak scaling) -- or --global-batch images (strong scaling, C4/C5) -- to tb200_graph_run, which shards dim 0
 over the GPUs; the weights are packed once and reach the other GPUs by ONE ncclBroadcast at prerun; no collective
-afterwards.  Under torchrun (one rank per GPU, as the driver launches it) rank 0 does this; the other ranks only take part
-in the process group's barriers.
+afterwards.  Under torchrun (one rank per GPU, as the driver launches it) rank 0 does this; the other ranks never touch a GPU:
+they follow rank 0 through the barriers it announces over a gloo process group and leave when it says so.
 """
 import argparse
 import json
@@ -245,6 +245,59 @@ def int8_tensor_peak(ctx=None):
     return 4500.0, "nominal dense int8 (B200_PROFILING.md)"
 
 
+# ---- rank protocol under torchrun (N > 1): a process group over gloo (CPU), so that the ranks which only wait never create a CUDA
+#      context or an NCCL kernel on "their" GPU -- rank 0's library is the only user of all N GPUs.  The leader announces every
+#      barrier before it enters it, so the followers do not need to know how many there are (a count mismatch between the two
+#      roles is a dead-lock that only shows on a multi-GPU box). ----
+class RankLead:
+    def __init__(self, world, devices):
+        self.world, self.devices = world, devices
+        if world > 1:
+            import datetime
+
+            import torch.distributed as dist
+
+            dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=60))
+
+    def barrier(self):
+        import torch
+
+        if torch.cuda.is_available():
+            for d in self.devices:
+                torch.cuda.synchronize(d)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast_object_list(["barrier"], src=0)
+            dist.barrier()
+
+    def finish(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast_object_list(["exit"], src=0)
+            dist.destroy_process_group()
+
+
+def rank_follow(world):
+    """Every rank but 0: meet rank 0 at each barrier it announces, leave when it says so."""
+    import datetime
+
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=60))
+    n = 0
+    while True:
+        cmd = [None]
+        dist.broadcast_object_list(cmd, src=0)
+        if cmd[0] != "barrier":
+            break
+        dist.barrier()
+        n += 1
+    dist.destroy_process_group()
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,7 +310,13 @@ def main():
     ap.add_argument("--no-tensorcore", action="store_true", help="route convs through the CUDA-core cross-check kernels")
     ap.add_argument("--cpu-window", type=float, default=12.0, help="cpu_baseline: length of the fleet window in seconds; 0 disables")
     ap.add_argument("--pinned", action="store_true", help="e2e with cudaHostAlloc'd caller buffers instead of pageable ones")
+    ap.add_argument("--watchdog", type=float, default=900.0, help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
     args = ap.parse_args()
+    if args.watchdog > 0 and int(os.environ.get("RANK", "0")) == 0:
+        import faulthandler
+
+        # a hung driver call must not hold the box forever (the followers of rank 0 are torn down by torchrun when it exits)
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
 
     if args.workload not in WORKLOADS:
         raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(WORKLOADS)}")
@@ -273,29 +332,27 @@ def main():
         run_reference_arm(args, rank)
         return
 
+    # The product shards the batch over the GPUs INSIDE one process (SURVEY.md 8(e): one tb200 context over N GPUs behind
+    # tb200_graph_run).  Under torchrun the driver starts one rank per GPU: rank 0 drives all N GPUs through the library; the other
+    # ranks never touch a GPU, they follow rank 0 through its barriers (rank_follow) and exit when it says so.
+    ngpu = max(1, args.gpus)
+    if rank != 0:
+        rank_follow(world)
+        return
+    lead = RankLead(world, [0] if ngpu == 1 else list(range(ngpu)))
+    try:
+        import torch
+
+        torch.cuda.set_device(0)
+        run_product_arm(args, ngpu, world, lead.barrier)
+    finally:
+        lead.finish()  # also on an exception: the followers must not be left waiting
+
+
+def run_product_arm(args, ngpu, world, barrier):
     import torch
-    import torch.distributed as dist
     from tengine_b200 import abi
     from tengine_b200 import runtime as rt
-
-    # The product shards the batch over the GPUs INSIDE one process (SURVEY.md 8(e): one tb200 context over N GPUs behind
-    # tb200_graph_run).  Under torchrun the driver starts one rank per GPU: rank 0 drives all N GPUs through the library, the
-    # other ranks join the process group (NCCL), meet rank 0 at the two barriers around the timed regions and exit.
-    ngpu = max(1, args.gpus)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    if rank != 0:
-        for _ in range(3):
-            barrier()
-        dist.destroy_process_group()
-        return
 
     strong = args.global_batch > 0
     total_batch = args.global_batch if strong else args.batch * ngpu
@@ -460,9 +517,6 @@ def main():
     print(json.dumps(line), flush=True)
     graph.close()
     ctx.close()
-    barrier()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -403,12 +403,10 @@ cudaError_t launch_conv_window(const WindowPlan& p, const void* w, void* out, co
 #define TB200_WIN_CASE(MD, U, LY)                                                                                                           \
     if (mode == MD && (e.is_uint8 != 0) == U && p.layout == LY)                                                                             \
     {                                                                                                                                       \
-        static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                                           \
-        if (!attr_dev[current_device() & 63])                                                                                                                          \
+        /* the opt-in is per device AND per context: set it before every launch (launches happen at graph capture only) */ \
         {                                                                                                                                   \
             cudaError_t err = cudaFuncSetAttribute(conv_window_tc_kernel<MD, U, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
             if (err != cudaSuccess) return err;                                                                                             \
-            attr_dev[current_device() & 63] = true;                                                                                                                    \
         }                                                                                                                                   \
         conv_window_tc_kernel<MD, U, LY><<<grid, 128, (size_t)p.smem_bytes, st>>>(tm, a, e);                                                \
         return cudaGetLastError();                                                                                                          \

@@ -80,6 +80,13 @@ struct tb200_context
     void* fixq = nullptr; // scratch of the GEMM kernels' deferred rare path: FIXQ_CAP entries per SM (gemm_tcgen05.cu)
 };
 static constexpr int FIXQ_CAP = 4096;
+// TB200_DEBUG_STAGES=1: progress lines of the multi-GPU set-up on stderr (which call a hang or an error sits in)
+#define STAGE(...)                                                                  \
+    do                                                                              \
+    {                                                                               \
+        static const bool on_ = getenv("TB200_DEBUG_STAGES") != nullptr;             \
+        if (on_) fprintf(stderr, "tengine_b200 stage: " __VA_ARGS__), fputc('\n', stderr), fflush(stderr); \
+    } while (0)
 
 // ---- NCCL, loaded at run time (libnccl.so.2: the copy torch already mapped when running under Python, the system one
 //      otherwise) so that single-GPU users never need it.  Only what the one broadcast at prerun needs. ----
@@ -101,8 +108,12 @@ static NcclApi* nccl_api()
     if (tried) return api.ok ? &api : nullptr;
     tried = true;
     if (getenv("TB200_NO_NCCL")) return nullptr;
+    // TB200_NCCL_LIB names the copy to use; else whatever "libnccl.so.2" resolves to -- a copy the process has already mapped (the one
+    // torch bundles, when running under Python: tengine_b200/runtime.py maps it first on purpose) or the system one
+    const char* forced = getenv("TB200_NCCL_LIB");
+    if (forced && *forced) api.handle = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
     for (const char* name : {"libnccl.so.2", "libnccl.so"})
-        if ((api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+        if (!api.handle) api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
     if (!api.handle) return nullptr;
     api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.handle, "ncclCommInitAll");
     api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
@@ -308,7 +319,9 @@ int tb200_context_create_multi(const int* cuda_devices, int num_devices, tb200_c
         if (nc)
         {
             std::vector<void*> comms(num_devices, nullptr);
+            STAGE("ncclCommInitAll over %d devices ...", num_devices);
             const int r = nc->CommInitAll(comms.data(), num_devices, cuda_devices);
+            STAGE("ncclCommInitAll -> %d", r);
             if (r == 0)
                 root->comms = comms, root->bcast_kind = "nccl";
             else
@@ -1718,6 +1731,7 @@ static int broadcast_arena(tb200_graph* g)
     NcclApi* nc = root->comms.empty() ? nullptr : nccl_api();
     if (nc)
     {
+        STAGE("grouped ncclBroadcast of %zu bytes ...", g->w_bytes);
         int r = nc->GroupStart();
         if (r == 0) r = nc->Broadcast(g->w_arena, g->w_arena, g->w_bytes, /*ncclUint8*/ 1, 0, root->comms[0], root->stream);
         for (size_t i = 0; r == 0 && i < g->shards.size(); i++)
@@ -1727,6 +1741,7 @@ static int broadcast_arena(tb200_graph* g)
             r = nc->Broadcast(sh->w_arena, sh->w_arena, sh->w_bytes, 1, 0, root->comms[i + 1], sh->ctx->stream);
         }
         const int r2 = nc->GroupEnd();
+        STAGE("ncclGroupEnd -> %d / %d", r, r2);
         if (r || r2) return fail(TB200_ERR_CUDA, "ncclBroadcast of the weight arena failed: %s", nc->GetErrorString(r ? r : r2));
     }
     else
@@ -1740,6 +1755,7 @@ static int broadcast_arena(tb200_graph* g)
     }
     CUDA_OK(cudaSetDevice(root->device));
     CUDA_OK(cudaStreamSynchronize(root->stream));
+    STAGE("broadcast: root stream drained");
     for (tb200_graph* sh : g->shards)
     {
         CUDA_OK(cudaSetDevice(sh->ctx->device));

@@ -51,6 +51,22 @@ static constexpr int PAR_MAX = 2048; // channels whose epilogue constants stay r
 static constexpr int MAX_STAGES = 24;
 static constexpr int B_RESIDENT_MAX = 96 * 1024; // weights of the CTA's N tile stay in smem when they fit in this many bytes
 
+// Diagnosis of a failed (or, with TB200_DEBUG_LAUNCH, every) GEMM launch: device, stream's device, limits and what was asked for.
+static void gemm_launch_debug(const void* fn, const char* what, cudaError_t err, int grid, size_t smem, cudaStream_t st)
+{
+    int dev = -1, optin = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncAttributes fa{};
+    const cudaError_t e2 = cudaFuncGetAttributes(&fa, fn);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    fprintf(stderr, "tengine_b200: gemm %s -> %s | device %d (%d SMs, opt-in smem %d) grid %d dynamic smem %zu | kernel static smem %zu max dynamic %d regs %d (%s) | capturing %d\n",
+            what, cudaGetErrorString(err), dev, sms, optin, grid, smem, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.numRegs, cudaGetErrorString(e2), (int)cap);
+    cudaGetLastError();
+}
+
 struct GemmArgs
 {
     int m_tiles, num_super; // 32-bit on purpose: 64-bit divisions in the tile decode cost ~100 instructions each
@@ -138,6 +154,24 @@ __device__ __forceinline__ bool fixq_push(uint32_t mtile, int oc, int32_t acc)
     return true;
 }
 
+#ifdef TB200_FIXQ_WORD
+// Variant: the lane queues all four elements of a guarded word as they are (one shared-memory atomic, four 16-byte stores, no call,
+// no parameter reload) and the drain re-derives which of them sit in the band.  Returns false when the queue cannot take them.
+__device__ __forceinline__ bool fixq_push_word(uint32_t mtile, int oc0, int32_t a0, int32_t a1, int32_t a2, int32_t a3)
+{
+    uint4* q = s_fixq.q;
+    if (!q) return false;
+    const uint32_t slot = atomicAdd(&s_fixq.count, 4u);
+    if (slot + 4u > s_fixq.cap) return false;
+    const uint32_t row = ((threadIdx.x >> 5) & 3u) * 32u + (threadIdx.x & 31u);
+    q[slot] = make_uint4(mtile, row | ((uint32_t)oc0 << 8), (uint32_t)a0, 1u);
+    q[slot + 1] = make_uint4(mtile, row | ((uint32_t)(oc0 + 1) << 8), (uint32_t)a1, 1u);
+    q[slot + 2] = make_uint4(mtile, row | ((uint32_t)(oc0 + 2) << 8), (uint32_t)a2, 1u);
+    q[slot + 3] = make_uint4(mtile, row | ((uint32_t)(oc0 + 3) << 8), (uint32_t)a3, 1u);
+    return true;
+}
+#endif
+
 // One guarded word (final fast bytes in `word`): find the elements that really sit in the band, queue them (or fix them here).
 // a[j]: what the fast path converted to float -- int8: the raw accumulator (y is added inside), uint8: accumulator + sum(x) term + y.
 template <bool U8, bool FUSE>
@@ -168,7 +202,7 @@ __device__ __noinline__ uint32_t gemm_fix_word(uint32_t word, int32_t a0, int32_
 }
 
 // After the CTA's last tile (every epilogue warp has waited for its own bulk stores): recompute the queued elements, one per thread.
-template <bool U8>
+template <bool U8, bool FUSE>
 __device__ __forceinline__ void fixq_drain(const GemmArgs& g, const EpiParams& e)
 {
     const uint32_t n = s_fixq.count < s_fixq.cap ? s_fixq.count : s_fixq.cap;
@@ -189,6 +223,17 @@ __device__ __forceinline__ void fixq_drain(const GemmArgs& g, const EpiParams& e
             else pix = ((long long)cn0 * g.oh + coh0) * g.ow + cow0 + r, ok = ok && cow0 + r < g.ow;
         }
         if (!ok || oc >= g.oc) continue; // a row the TMA store clipped
+        if (q.w)
+        {
+            // a whole guarded word was queued: is this element inside the band?  (same t as the fast path)
+            // fast_par is float4[OCp/2] = { M[2k], M[2k+1], y[2k], y[2k+1] }
+            const float* fp = reinterpret_cast<const float*>(e.fast_par) + (oc >> 1) * 4 + (oc & 1);
+            const float2 my = make_float2(__ldg(fp), __ldg(fp + 2));
+            const int32_t a = (int32_t)q.z;
+            const float t = U8 ? __fmul_rn((float)a, my.x) : (FUSE ? __fmaf_rn((float)a, my.x, my.y) : __fmul_rn((float)(a + __float_as_int(my.y)), my.x));
+            const float r2 = __fadd_rn(t, TB200_MAGIC);
+            if (!(fabsf(__fsub_rn(t, __fsub_rn(r2, TB200_MAGIC))) > 0.5f - TB200_TIE_EPS)) continue;
+        }
         const int32_t acc = (int32_t)q.z - ((U8 && e.has_bias) ? __ldg(e.bias + oc) : 0);
         g.out_base[(size_t)pix * g.ldo + oc] = (uint8_t)requant(acc, oc, e);
     }
@@ -221,7 +266,12 @@ __device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (gw[j] > 0.5f - TB200_TIE_EPS)
+            {
+#ifdef TB200_FIXQ_WORD
+                if (fixq_push_word(mtile, oc0 + j * 4, (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3])) continue;
+#endif
                 w[j] = gemm_fix_word<false, FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, 0x7fffffff /* pad channels have M = y = 0: never guarded */, mtile, e);
+            }
     }
     sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
@@ -300,6 +350,9 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
                         const int4 c = __ldg(reinterpret_cast<const int4*>(g.btab + (size_t)pad_mask * g.ocp + oc0 + j * 4));
                         a[0] += c.x, a[1] += c.y, a[2] += c.z, a[3] += c.w;
                     }
+#ifdef TB200_FIXQ_WORD
+                    if (fixq_push_word(mtile, oc0 + j * 4, a[0], a[1], a[2], a[3])) continue;
+#endif
                     w[j] = gemm_fix_word<true, false>(w[j], a[0], a[1], a[2], a[3], oc0 + j * 4, g.oc, mtile, e);
                 }
         }
@@ -734,7 +787,7 @@ __global__ void __launch_bounds__(U8 ? GEMM_THREADS_U8 : GEMM_THREADS, 1)
             // deferred rare path: every warp's stores are complete (and its queue entries written) once all have passed this barrier
             __threadfence_block();
             epilogue_bar_sync();
-            fixq_drain<U8>(g, e);
+            fixq_drain<U8, MODE == 1>(g, e);
         }
     }
 
@@ -1284,12 +1337,10 @@ cudaError_t launch_conv_gather_tc(const void* in, const void* w, void* out, cons
 #define TB200_GAT_CASE(MD, U, K)                                                                                                   \
     if (mode == MD && (e.is_uint8 != 0) == U && khw == K)                                                                          \
     {                                                                                                                              \
-        static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                                  \
-        if (!attr_dev[current_device() & 63])                                                                                                                 \
+        /* the opt-in is per device AND per context: set it before every launch (launches happen at graph capture only) */ \
         {                                                                                                                          \
             cudaError_t err = cudaFuncSetAttribute(conv_gather_tc_kernel<MD, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
             if (err != cudaSuccess) return err;                                                                                    \
-            attr_dev[current_device() & 63] = true;                                                                                                           \
         }                                                                                                                          \
         conv_gather_tc_kernel<MD, U, K><<<grid, 128, smem, st>>>(a, e);                                                            \
         return cudaGetLastError();                                                                                                 \
@@ -1824,12 +1875,10 @@ static cudaError_t launch_gemm_simple(const GemmPlan& p, const EpiParams& e, int
 #define TB200_SIMPLE_CASE(MD)                                                                                                  \
     if (mode == MD)                                                                                                            \
     {                                                                                                                          \
-        static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                              \
-        if (!attr_dev[current_device() & 63])                                                                                                             \
+        /* the opt-in is per device AND per context: set it before every launch (launches happen at graph capture only) */ \
         {                                                                                                                      \
             cudaError_t err = cudaFuncSetAttribute(gemm_simple_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024); \
             if (err != cudaSuccess) return err;                                                                                \
-            attr_dev[current_device() & 63] = true;                                                                                                       \
         }                                                                                                                      \
         gemm_simple_kernel<MD><<<grid, 128, smem, st>>>(ta, tb, g, e);                                                         \
         return cudaGetLastError();                                                                                             \
@@ -1872,6 +1921,7 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
                         (size_t)EPI_WARPS * 2 * 512 * (p.cs == 8 ? 4 : p.cs) + sizeof(GemmSmemCtl) +
                         (size_t)(g.par_all ? par_ch : p.block_n) * 8 + 1024;
     static const bool trace_on = getenv("TB200_GEMM_TRACE") != nullptr;
+    static const bool launch_dbg = getenv("TB200_DEBUG_LAUNCH") != nullptr;
     static unsigned long long* trace_buf = nullptr;
     g.trace = nullptr;
     if (trace_on)
@@ -1894,16 +1944,17 @@ cudaError_t launch_gemm_i8(const GemmPlan& p, const EpiParams& e, const int32_t*
 #define TB200_GEMM_CASE(U, MD, C, B)                                                                                           \
     if ((p.u8 != 0) == U && mode == MD && p.cs == C && border == B)                                                            \
     {                                                                                                                          \
-        static bool attr_dev[64] = {};            /* the opt-in is per device */                                                                                              \
-        if (!attr_dev[current_device() & 63])                                                                                                             \
+        /* the opt-in is per device AND per context: set it before every launch (launches happen at graph capture only) */ \
         {                                                                                                                      \
             err = cudaFuncSetAttribute(gemm_i8_tcgen05_kernel<U, MD, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            if (launch_dbg) gemm_launch_debug((const void*)gemm_i8_tcgen05_kernel<U, MD, C, B>, "set attribute", err, grid, smem, st);    \
             if (err != cudaSuccess) return err;                                                                                \
-            attr_dev[current_device() & 63] = true;                                                                                                       \
         }                                                                                                                      \
         gemm_i8_tcgen05_kernel<U, MD, C, B><<<grid, U ? GEMM_THREADS_U8 : GEMM_THREADS, smem, st>>>(ta, tb, to, tt, g, e);                           \
         if (trace_on) gemm_trace_report(p, g, grid, st);                                                                       \
-        return cudaGetLastError();                                                                                             \
+        err = cudaGetLastError();                                                                                              \
+        if (launch_dbg || err != cudaSuccess) gemm_launch_debug((const void*)gemm_i8_tcgen05_kernel<U, MD, C, B>, "launch", err, grid, smem, st); \
+        return err;                                                                                                            \
     }
 #define TB200_GEMM_CS(U, MD, B) TB200_GEMM_CASE(U, MD, 1, B) TB200_GEMM_CASE(U, MD, 2, B) TB200_GEMM_CASE(U, MD, 4, B) TB200_GEMM_CASE(U, MD, 8, B)
     TB200_GEMM_CS(false, 0, false)

@@ -55,9 +55,6 @@ def _worker(rank, world, port, q):
         # ... and the slices land in one buffer at the offsets the rule gives (all_gather stands in for the host buffer here)
         gathered = [None] * world
         dist.all_gather_object(gathered, (start, out))
-        # the barrier protocol of bench.py: three barriers, only rank 0 works between them
-        for _ in range(3):
-            dist.barrier()
         q.put((rank, gathered))
     finally:
         dist.destroy_process_group()
@@ -85,3 +82,41 @@ def test_world_size_2_gloo_slices_equal_the_whole_batch(oracle):
         for start, out in gathered:
             got[start:start + out.shape[0]] = out
         assert np.array_equal(got, want), rank
+
+
+def _bench_rank(rank, world, port, q):
+    """bench.py's own rank protocol (the code the driver's torchrun launch executes), without a GPU: the leader announces each of
+    its barriers, the followers meet it there and leave when told -- whatever the number of barriers."""
+    import sys
+
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank)})
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    if rank == 0:
+        lead = bench.RankLead(world, [0])
+        try:
+            for _ in range(5):
+                lead.barrier()
+        finally:
+            lead.finish()
+        q.put((rank, 5))
+    else:
+        q.put((rank, bench.rank_follow(world)))
+
+
+def test_bench_rank_protocol_world_size_3_gloo():
+    import torch.multiprocessing as mp
+
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bench_rank, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == {0: 5, 1: 5, 2: 5}  # every follower met the leader at each of its barriers and then left

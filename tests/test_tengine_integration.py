@@ -14,6 +14,20 @@ BUILD = os.path.join(ROOT, "build", "tengine")
 MODELS = os.path.join(ROOT, "oracle", "_ref", "models")
 
 
+def _refresh_cuda_library_copy():
+    """libtengine-lite.so finds the CUDA library beside itself (rpath $ORIGIN): that copy must be THE library under test, not the
+    one of the last integration build (a stale copy once hid a multi-GPU fix from the unmodified-app tests)."""
+    import filecmp
+    import shutil
+
+    src, dst = os.path.join(ROOT, "tengine_b200", "libtengine_b200.so"), os.path.join(BUILD, "libtengine_b200.so")
+    if os.path.isdir(BUILD) and os.path.exists(src) and not (os.path.exists(dst) and filecmp.cmp(src, dst, shallow=False)):
+        shutil.copy2(src, dst)
+
+
+_refresh_cuda_library_copy()
+
+
 def _have_integration():
     return os.path.exists(os.path.join(BUILD, "libtengine-lite.so")) and os.path.exists(os.path.join(BUILD, "libref_shim.so"))
 
