@@ -154,24 +154,6 @@ __device__ __forceinline__ bool fixq_push(uint32_t mtile, int oc, int32_t acc)
     return true;
 }
 
-#ifdef TB200_FIXQ_WORD
-// Variant: the lane queues all four elements of a guarded word as they are (one shared-memory atomic, four 16-byte stores, no call,
-// no parameter reload) and the drain re-derives which of them sit in the band.  Returns false when the queue cannot take them.
-__device__ __forceinline__ bool fixq_push_word(uint32_t mtile, int oc0, int32_t a0, int32_t a1, int32_t a2, int32_t a3)
-{
-    uint4* q = s_fixq.q;
-    if (!q) return false;
-    const uint32_t slot = atomicAdd(&s_fixq.count, 4u);
-    if (slot + 4u > s_fixq.cap) return false;
-    const uint32_t row = ((threadIdx.x >> 5) & 3u) * 32u + (threadIdx.x & 31u);
-    q[slot] = make_uint4(mtile, row | ((uint32_t)oc0 << 8), (uint32_t)a0, 1u);
-    q[slot + 1] = make_uint4(mtile, row | ((uint32_t)(oc0 + 1) << 8), (uint32_t)a1, 1u);
-    q[slot + 2] = make_uint4(mtile, row | ((uint32_t)(oc0 + 2) << 8), (uint32_t)a2, 1u);
-    q[slot + 3] = make_uint4(mtile, row | ((uint32_t)(oc0 + 3) << 8), (uint32_t)a3, 1u);
-    return true;
-}
-#endif
-
 // One guarded word (final fast bytes in `word`): find the elements that really sit in the band, queue them (or fix them here).
 // a[j]: what the fast path converted to float -- int8: the raw accumulator (y is added inside), uint8: accumulator + sum(x) term + y.
 template <bool U8, bool FUSE>
@@ -202,7 +184,7 @@ __device__ __noinline__ uint32_t gemm_fix_word(uint32_t word, int32_t a0, int32_
 }
 
 // After the CTA's last tile (every epilogue warp has waited for its own bulk stores): recompute the queued elements, one per thread.
-template <bool U8, bool FUSE>
+template <bool U8>
 __device__ __forceinline__ void fixq_drain(const GemmArgs& g, const EpiParams& e)
 {
     const uint32_t n = s_fixq.count < s_fixq.cap ? s_fixq.count : s_fixq.cap;
@@ -223,17 +205,6 @@ __device__ __forceinline__ void fixq_drain(const GemmArgs& g, const EpiParams& e
             else pix = ((long long)cn0 * g.oh + coh0) * g.ow + cow0 + r, ok = ok && cow0 + r < g.ow;
         }
         if (!ok || oc >= g.oc) continue; // a row the TMA store clipped
-        if (q.w)
-        {
-            // a whole guarded word was queued: is this element inside the band?  (same t as the fast path)
-            // fast_par is float4[OCp/2] = { M[2k], M[2k+1], y[2k], y[2k+1] }
-            const float* fp = reinterpret_cast<const float*>(e.fast_par) + (oc >> 1) * 4 + (oc & 1);
-            const float2 my = make_float2(__ldg(fp), __ldg(fp + 2));
-            const int32_t a = (int32_t)q.z;
-            const float t = U8 ? __fmul_rn((float)a, my.x) : (FUSE ? __fmaf_rn((float)a, my.x, my.y) : __fmul_rn((float)(a + __float_as_int(my.y)), my.x));
-            const float r2 = __fadd_rn(t, TB200_MAGIC);
-            if (!(fabsf(__fsub_rn(t, __fsub_rn(r2, TB200_MAGIC))) > 0.5f - TB200_TIE_EPS)) continue;
-        }
         const int32_t acc = (int32_t)q.z - ((U8 && e.has_bias) ? __ldg(e.bias + oc) : 0);
         g.out_base[(size_t)pix * g.ldo + oc] = (uint8_t)requant(acc, oc, e);
     }
@@ -266,12 +237,7 @@ __device__ __forceinline__ void epilogue_unit_fast(const uint32_t (&v)[16], uint
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (gw[j] > 0.5f - TB200_TIE_EPS)
-            {
-#ifdef TB200_FIXQ_WORD
-                if (fixq_push_word(mtile, oc0 + j * 4, (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3])) continue;
-#endif
                 w[j] = gemm_fix_word<false, FUSE>(w[j], (int32_t)v[j * 4], (int32_t)v[j * 4 + 1], (int32_t)v[j * 4 + 2], (int32_t)v[j * 4 + 3], oc0 + j * 4, 0x7fffffff /* pad channels have M = y = 0: never guarded */, mtile, e);
-            }
     }
     sts_u4(dst_addr, w[0], w[1], w[2], w[3]);
 }
@@ -350,9 +316,6 @@ __device__ __forceinline__ void epilogue_unit_u8(const uint32_t (&v)[16], int32_
                         const int4 c = __ldg(reinterpret_cast<const int4*>(g.btab + (size_t)pad_mask * g.ocp + oc0 + j * 4));
                         a[0] += c.x, a[1] += c.y, a[2] += c.z, a[3] += c.w;
                     }
-#ifdef TB200_FIXQ_WORD
-                    if (fixq_push_word(mtile, oc0 + j * 4, a[0], a[1], a[2], a[3])) continue;
-#endif
                     w[j] = gemm_fix_word<true, false>(w[j], a[0], a[1], a[2], a[3], oc0 + j * 4, g.oc, mtile, e);
                 }
         }
@@ -787,7 +750,7 @@ __global__ void __launch_bounds__(U8 ? GEMM_THREADS_U8 : GEMM_THREADS, 1)
             // deferred rare path: every warp's stores are complete (and its queue entries written) once all have passed this barrier
             __threadfence_block();
             epilogue_bar_sync();
-            fixq_drain<U8, MODE == 1>(g, e);
+            fixq_drain<U8>(g, e);
         }
     }
 
