@@ -249,6 +249,12 @@ def int8_tensor_peak(ctx=None):
 #      context or an NCCL kernel on "their" GPU -- rank 0's library is the only user of all N GPUs.  The leader announces every
 #      barrier before it enters it, so the followers do not need to know how many there are (a count mismatch between the two
 #      roles is a dead-lock that only shows on a multi-GPU box). ----
+def _gloo_on_loopback():
+    """All ranks live on one node (the bench contract): bind gloo to the loopback interface instead of whatever the container's
+    hostname resolves to (it may not resolve at all)."""
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+
+
 class RankLead:
     def __init__(self, world, devices):
         self.world, self.devices = world, devices
@@ -257,6 +263,7 @@ class RankLead:
 
             import torch.distributed as dist
 
+            _gloo_on_loopback()
             dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=60))
 
     def barrier(self):
@@ -285,6 +292,7 @@ def rank_follow(world):
 
     import torch.distributed as dist
 
+    _gloo_on_loopback()
     dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=60))
     n = 0
     while True:
