@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--no-tensorcore", action="store_true", help="route convs through the CUDA-core cross-check kernels")
     ap.add_argument("--cpu-window", type=float, default=12.0, help="cpu_baseline: length of the fleet window in seconds; 0 disables")
     ap.add_argument("--pinned", action="store_true", help="e2e with cudaHostAlloc'd caller buffers instead of pageable ones")
-    ap.add_argument("--watchdog", type=float, default=900.0, help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
+    ap.add_argument("--watchdog", type=float, default=780.0, help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
     args = ap.parse_args()
     if args.watchdog > 0 and int(os.environ.get("RANK", "0")) == 0:
         import faulthandler
