@@ -204,6 +204,23 @@ def build_apps(ref="/root/reference", verbose=True):
             print(f"[oracle] WARNING: could not build {name}:\n{r.stderr[-1500:]}", file=sys.stderr)
             continue
         built.append(out)
+    # the detection post-processing of the unmodified YOLOv3-tiny example, callable (oracle/yolo_example_shim.cpp): its source needs
+    # C++ OpenCV, replaced here by the minimal stand-in headers of oracle/cvstub (only cv::Rect_ carries semantics)
+    here = os.path.dirname(os.path.abspath(__file__))
+    shim, out = os.path.join(here, "yolo_example_shim.cpp"), os.path.join(OUT, "libyolo_example.so")
+    example = f"{ref}/examples/tm_yolov3_tiny_uint8.cpp"
+    if os.path.exists(shim) and os.path.exists(example):
+        if not (os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in (shim, example, os.path.join(here, "cvstub/opencv2/core/core.hpp")))):
+            ops_o = os.path.join(OUT, "yolo_example_tengine_operations.o")  # helpers the example's main() calls (C source of the reference)
+            r = subprocess.run([CC, "-O2", "-w", "-std=gnu99", "-fPIC", "-c"] + inc + [f"{ref}/examples/common/tengine_operations.c", "-o", ops_o], capture_output=True, text=True)
+            cmd = [CXX, "-O2", "-w", "-std=c++11", "-fPIC", "-shared", f"-I{os.path.join(here, 'cvstub')}"] + inc + [shim, ops_o, "-o", out, f"-L{OUT}", "-ltengine-lite",
+                                                                                                                   "-Wl,-rpath,$ORIGIN", "-lm"]
+            if r.returncode == 0:
+                r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                print(f"[oracle] WARNING: could not build libyolo_example.so:\n{r.stderr[-1500:]}", file=sys.stderr)
+        if os.path.exists(out):
+            built.append(out)
     if verbose:
         print("[oracle] apps:", ", ".join(os.path.basename(b) for b in built))
     return built

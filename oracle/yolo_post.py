@@ -2,19 +2,30 @@
 tb200_graph_yolo_detect):  dequantisation (:464-478), generate_proposals (:176-250), qsort_descent_inplace (:57-100),
 nms_sorted_bboxes (:102-132), cv::Rect_<float> intersection / area.
 
-PARITY UNPINNED: the example needs C++ OpenCV, which this image lacks, so it cannot be built and run here; its sources embed no
-golden vectors.  Arithmetic follows the source text: `exp()` resolves to the C library's double exp (the file includes no
-<cmath> overloads into the global namespace; the explicit static_cast<float> in sigmoid() says the same), float everywhere else.
+PINNED (round 2): tests/test_yolo_post_pinned.py compares this file, box for box and bit for bit, with the example's own functions
+compiled from the unmodified source (oracle/yolo_example_shim.cpp + oracle/cvstub, built into oracle/_ref/libyolo_example.so) and
+with a committed fixture of their output.  What the pin corrected: `exp()` on a float argument resolves to the FLOAT overload in
+that translation unit (its <cmath> / <math.h> bring std::exp(float) into scope), so sigmoid and exp(dw) * anchor are float
+arithmetic throughout -- not double, as a reading of the text suggested.  expf comes from the C library (ctypes), the same function
+the compiled example and the device's host-side table builder call.
 """
-import math
+import ctypes
+import ctypes.util
 
 import numpy as np
 
 f32 = np.float32
+_libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+_libm.expf.restype = ctypes.c_float
+_libm.expf.argtypes = [ctypes.c_float]
+
+
+def _expf(x):
+    return f32(_libm.expf(float(f32(x))))
 
 
 def _sigmoid(x):
-    return f32(1.0 / (1.0 + math.exp(-float(x))))  # static_cast<float>(1.f / (1.f + exp(-x))) with double exp
+    return f32(f32(1.0) / f32(f32(1.0) + _expf(-f32(x))))  # static_cast<float>(1.f / (1.f + exp(-x))), exp = the float overload
 
 
 def generate_proposals(stride, feat, anchors6, num_classes, prob_threshold):
@@ -33,8 +44,8 @@ def generate_proposals(stride, feat, anchors6, num_classes, prob_threshold):
                     dw, dh = feat[a * per + 2, h, w], feat[a * per + 3, h, w]
                     pred_x = f32(f32(f32(w) + dx) * f32(stride))
                     pred_y = f32(f32(f32(h) + dy) * f32(stride))
-                    pred_w = f32(math.exp(float(dw)) * float(f32(anchors6[2 * a])))      # double product, narrowed on assignment
-                    pred_h = f32(math.exp(float(dh)) * float(f32(anchors6[2 * a + 1])))
+                    pred_w = f32(_expf(dw) * f32(anchors6[2 * a]))      # float exp(dw) * anchor_w
+                    pred_h = f32(_expf(dh) * f32(anchors6[2 * a + 1]))
                     x0, y0 = f32(pred_x - f32(pred_w * f32(0.5))), f32(pred_y - f32(pred_h * f32(0.5)))
                     x1, y1 = f32(pred_x + f32(pred_w * f32(0.5))), f32(pred_y + f32(pred_h * f32(0.5)))
                     out.append([x0, y0, f32(x1 - x0), f32(y1 - y0), final, cls])

@@ -2195,8 +2195,13 @@ static void build_yolo_tables(const tb200_tensor_desc& d, float* sig, double* ex
     {
         const float q = d.data_type == TB200_DT_UINT8 ? (float)b : (float)(int)(int8_t)b;
         volatile float x = (q - (float)d.zero_point) * d.scale;
-        sig[b] = (float)(1.f / (1.f + exp((double)-x)));
-        ex[b] = exp((double)x);
+        // The example's `exp(-x)` / `exp(dw)` on a float argument resolve to the float overload (its <cmath> / <math.h> put std::exp(float)
+        // in scope): float arithmetic throughout -- pinned by compiling the unmodified example (oracle/yolo_example_shim.cpp,
+        // tests/test_yolo_post_pinned.py).  The product exp(dw) * anchor is then a float product: held as a double here, the
+        // kernel's double multiply of two float values is exact and its narrowing rounds once, like the float multiply.
+        volatile float e_neg = expf(-x), e_pos = expf(x);
+        sig[b] = 1.f / (1.f + e_neg);
+        ex[b] = (double)e_pos;
     }
 }
 

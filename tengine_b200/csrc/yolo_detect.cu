@@ -15,7 +15,7 @@ namespace tb200 {
 // ---- decode: one thread per (image, cell, anchor) of one head ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) yolo_decode_kernel(const uint8_t* __restrict__ t, int cp, int H, int W, int n_img, int anchors_n, int classes,
                                                           const float* __restrict__ sig,  // [256]: sigmoid(dequantised byte), as a float
-                                                          const double* __restrict__ ex,  // [256]: exp(dequantised byte), in double like the example's exp()
+                                                          const double* __restrict__ ex,  // [256]: the example's float exp(dequantised byte), held as a double
                                                           float stride, float a0w, float a0h, float a1w, float a1h, float a2w, float a2h, float thr,
                                                           YoloCand* __restrict__ cand, int* __restrict__ count, int max_cand, unsigned key_base, bool is_u8)
 {
@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const uint8_t* __restr
     const float dx = sig[p[0]], dy = sig[p[1]];
     const float aw = anchor == 0 ? a0w : (anchor == 1 ? a1w : a2w), ah = anchor == 0 ? a0h : (anchor == 1 ? a1h : a2h);
     const float pred_x = __fmul_rn(__fadd_rn((float)w, dx), stride), pred_y = __fmul_rn(__fadd_rn((float)h, dy), stride);
-    // `float pred_w = exp(dw) * anchor_w;` -- the product is formed in double, then narrowed
+    // `float pred_w = exp(dw) * anchor_w;` is a float product (exp resolves to the float overload there): the double product of two
+    // float values is exact, so narrowing it rounds once, exactly like the float multiply
     const float pred_w = (float)__dmul_rn(ex[p[2]], (double)aw), pred_h = (float)__dmul_rn(ex[p[3]], (double)ah);
     const float x0 = __fsub_rn(pred_x, __fmul_rn(pred_w, 0.5f)), y0 = __fsub_rn(pred_y, __fmul_rn(pred_h, 0.5f));
     const float x1 = __fadd_rn(pred_x, __fmul_rn(pred_w, 0.5f)), y1 = __fadd_rn(pred_y, __fmul_rn(pred_h, 0.5f));
