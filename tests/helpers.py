@@ -22,7 +22,8 @@ def quant_u8(x, scale, zp):
 
 
 def kat_graphs():
-    """Build (name, GraphDef, input, expected_real, tolerance) from tests/golden/reference_kats.json."""
+    """Build (name, GraphDef, inputs, expected_real, tolerance) from tests/golden/reference_kats.json (`inputs`: one array per graph
+    input)."""
     kats = json.load(open(os.path.join(GOLDEN, "reference_kats.json")))["kats"]
     out = []
     for k in kats:
@@ -32,10 +33,14 @@ def kat_graphs():
         x = g.input(n, c, h, w, k["input_scale"], k.get("input_zero", 0))
         if "input_q" in k:
             xin = np.array(k["input_q"], np.int8).reshape(n, c, h, w)
+        elif "input_real" in k:  # int8: idata = round(real / scale) (test_opendla_op_relu.cpp:150-156)
+            xin = np.clip(np.rint(np.array(k["input_real"], np.float64) / k["input_scale"]), -127, 127).astype(np.int8).reshape(n, c, h, w)
         elif "input_fill" in k:
             xin = quant_u8(np.full((n, c, h, w), k["input_fill"]), k["input_scale"], k["input_zero"])
         else:
             xin = quant_u8(k["input"], k["input_scale"], k["input_zero"]).reshape(n, c, h, w)
+        inputs = [xin]
+        oz = k.get("output_zero", 0)
         if k["op"] in ("conv", "fc"):
             if u8:
                 wq = quant_u8(k["weight"], k["weight_scale"], k["weight_zero"]).reshape(k["weight_dims"])
@@ -45,19 +50,38 @@ def kat_graphs():
                 ws, wz = k["weight_scales"], 0
             bq = np.array(k["bias_q"], np.int32) if "bias_q" in k else None
             if k["op"] == "conv":
-                y = g.conv(x, wq, bq, ws, k["output_scale"], k.get("output_zero", 0), stride=k["stride"], pad=k["pad"],
+                y = g.conv(x, wq, bq, ws, k["output_scale"], oz, stride=k["stride"], pad=k["pad"],
                            group=k["group"], activation=k["activation"], weight_zero=wz)
             else:
-                y = g.fc(x, wq, bq, ws, k["output_scale"], k.get("output_zero", 0), weight_zero=wz)
-        else:
+                y = g.fc(x, wq, bq, ws, k["output_scale"], oz, weight_zero=wz)
+        elif k["op"] == "pool":
             y = g.pool(x, abi.POOL_MAX if k["method"] == "max" else abi.POOL_AVG, k["kernel"], k["stride"], k["pad"],
-                       out_scale=k["output_scale"], out_zero=k.get("output_zero", 0))
+                       out_scale=k["output_scale"], out_zero=oz)
+        elif k["op"] == "hardswish":
+            y = g.hardswish(x, k["output_scale"], oz)
+        elif k["op"] == "sigmoid":
+            y = g.sigmoid(x, k["output_scale"], oz)
+        elif k["op"] == "softmax":
+            y = g.softmax(x, k["output_scale"], oz)
+        elif k["op"] == "relu":
+            y = g.relu(x, k["output_scale"], oz, negative_slope=k["negative_slope"])
+        elif k["op"] == "relu2_sum":  # test_opendla_op_eltwise.cpp: two ReLU nodes on the same input, summed
+            y = g.eltwise(g.relu(x, k["output_scale"], oz), g.relu(x, k["output_scale"], oz), k["output_scale"], oz, elt_type=abi.ELT_SUM)
+        elif k["op"] in ("eltwise", "concat"):
+            x1 = g.input(n, c, h, w, k["input1_scale"], k.get("input1_zero", 0))
+            inputs.append(quant_u8(k["input1"], k["input1_scale"], k["input1_zero"]).reshape(n, c, h, w))
+            if k["op"] == "eltwise":
+                y = g.eltwise(x, x1, k["output_scale"], oz, elt_type=abi.ELT_SUM if k["elt"] == "sum" else abi.ELT_PROD)
+            else:
+                y = g.concat([x, x1], k["output_scale"], oz)
+        else:
+            raise ValueError(k["op"])
         g.mark_output(y)
         if "expected_fill" in k:
             exp = np.full(g.dims(y), k["expected_fill"], np.float64)
         else:
             exp = np.array(k["expected"], np.float64).reshape(g.dims(y))
-        out.append((k["name"], g, xin, exp, k.get("tolerance", 0.1)))
+        out.append((k["name"], g, inputs, exp, k.get("tolerance", 0.1)))
     return out
 
 

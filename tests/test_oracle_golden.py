@@ -8,9 +8,9 @@ from tests.helpers import dequant, kat_graphs, layer_outputs, load_golden
 
 @pytest.mark.parametrize("kat", kat_graphs(), ids=lambda k: k[0])
 def test_oracle_reproduces_reference_kats(oracle, kat):
-    name, g, xin, expected, tol = kat
+    name, g, xins, expected, tol = kat
     for mode in (0, 1):
-        out = oracle.run(g, [xin], uint8_mode=mode)[g.outputs[0]]
+        out = oracle.run(g, xins, uint8_mode=mode)[g.outputs[0]]
         real = dequant(g, g.outputs[0], out)
         assert np.abs(real - expected).max() <= tol + 1e-6, (name, mode, real.ravel(), expected.ravel())
 
