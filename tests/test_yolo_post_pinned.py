@@ -44,3 +44,22 @@ def test_restatement_equals_the_compiled_example_live():
         want = gen.run_example(L, *heads)
         got = _restatement(*heads)
         assert got.shape == want.shape and np.array_equal(got, want), seed
+
+
+def test_device_table_arithmetic_equals_the_restatement():
+    """The device looks sigmoid / exp up in 256-entry tables built on the host (engine.cu build_yolo_tables: float expf, the exp table
+    held as doubles) and forms exp(dw) * anchor as a double product narrowed to float (yolo_detect.cu).  Emulated here in numpy for
+    every byte, both data types and all YOLOv3-tiny anchors: identical to the float arithmetic of the example / restatement."""
+    f32 = np.float32
+    for is_u8, zero, scale in ((True, 137, 0.0831), (False, 0, 0.0517), (True, 0, 0.19), (True, 255, 0.004)):
+        b = np.arange(256)
+        q = b.astype(np.float32) if is_u8 else b.astype(np.uint8).view(np.int8).astype(np.float32)
+        x = ((q - f32(zero)) * f32(scale)).astype(np.float32)
+        sig = np.array([f32(1.0) / f32(f32(1.0) + yolo_post._expf(-v)) for v in x], np.float32)   # the device's table
+        ex = np.array([np.float64(yolo_post._expf(v)) for v in x])                                  # (double)expf(x)
+        assert np.array_equal(sig, np.array([yolo_post._sigmoid(v) for v in x], np.float32))
+        for a in ANCHORS:
+            dev = (ex * np.float64(f32(a))).astype(np.float32)        # (float)__dmul_rn(ex, (double)anchor)
+            ref = np.array([f32(yolo_post._expf(v) * f32(a)) for v in x], np.float32)
+            same = (dev == ref) | (np.isinf(dev) & np.isinf(ref))
+            assert same.all(), (is_u8, zero, scale, a)
