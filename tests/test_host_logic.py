@@ -64,3 +64,20 @@ def test_reference_worker_is_torch_free_and_reports_json(tmp_path):
     assert r.returncode == 0, r.stderr[-800:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["images"] == 2 and out["loop_s"] > 0 and out["min_ms"] > 0
+
+
+def test_ncu_traffic_tool_reproduces_the_committed_traffic_file(tmp_path):
+    """tools/ncu_traffic_json.py on the committed per-launch summary of round 1's whole-step capture gives the committed per-family
+    DRAM bytes (the numbers bench.py reports as roofline.traffic)."""
+    import subprocess
+
+    out = tmp_path / "t.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic_json.py"), os.path.join(ROOT, "profiles", "r01_final_ncu_full_summary.csv"),
+                        str(out), "mobilenet_v1_int8", "256"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.load(open(out))
+    want = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    for fam, f in want["families"].items():
+        assert fam in got["families"], fam
+        assert got["families"][fam]["launches_per_step"] == f["launches_per_step"]
+        assert got["families"][fam]["dram_bytes_per_step"] == pytest.approx(f["dram_bytes_per_step"], rel=1e-6)
