@@ -10,6 +10,16 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # On a multi-GPU box some tests reach the library's NCCL path through the Tengine runtime (not through tengine_b200/runtime.py,
+    # which maps torch's bundled NCCL first): do the same here, once, so that a later `import torch` in this process still finds
+    # the NCCL build it was linked against (a process can hold only one libnccl.so.2).
+    try:
+        from tengine_b200 import runtime as rt
+
+        if os.path.exists(rt.LIB_PATH) and rt.device_count() > 1:
+            rt._preload_bundled_nccl()
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")
